@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+Run in the build container only (needs /root/reference and oracle/_ref):
+
+    bash oracle/build_ref.sh && python tests/golden/generate_golden.py
+
+Everything written here is an *output of the reference* (reference dpilqr/*.py +
+its compiled bbdynamics module) on seeded inputs; the fixtures are what pins the
+oracle (oracle/ilqr_oracle.py) and, through it and directly, the CUDA path.
+The per-iteration traces are obtained by wrapping ilqrSolver._backward_pass and
+ilqrSolver._forward_pass at class level.
+"""
+
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.ref_loader import load_reference  # noqa: E402
+
+ref = load_reference()
+OUT = os.path.dirname(os.path.abspath(__file__))
+G = 9.80665
+
+MODEL_CLASSES = {
+    "DoubleInt4D": ref.DoubleIntDynamics4D,
+    "DoubleInt6D": ref.DoubleIntDynamics6D,
+    "Car3D": ref.CarDynamics3D,
+    "Unicycle4D": ref.UnicycleDynamics4D,
+    "Quadcopter6D": ref.QuadcopterDynamics6D,
+    "Human6D": ref.HumanDynamics6D,
+    "HumanLin6D": ref.HumanDynamicsLin6D,
+    "Quadcopter12D": ref.QuadcopterDynamics12D,
+    "Bike5D": ref.BikeDynamics5D,
+}
+
+
+# --------------------------------------------------------------------------- #
+# instrumentation
+# --------------------------------------------------------------------------- #
+class Trace:
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        cls = ref.ilqrSolver
+        self._bp, self._fp, self._solve = cls._backward_pass, cls._forward_pass, cls.solve
+        trace = self
+        self.n_solves = 0
+
+        def solve(solver, *a, **kw):
+            trace.n_solves += 1
+            return trace._solve(solver, *a, **kw)
+
+        def bp(solver, X, U):
+            K, d = trace._bp(solver, X, U)
+            trace.records.append({"solver": trace.n_solves, "mu": solver.μ, "K": K, "d": d, "J": [], "alpha": []})
+            return K, d
+
+        def fp(solver, X, U, K, d, α):
+            out = trace._fp(solver, X, U, K, d, α)
+            trace.records[-1]["J"].append(out[2])
+            trace.records[-1]["alpha"].append(float(α))
+            return out
+
+        cls._backward_pass, cls._forward_pass, cls.solve = bp, fp, solve
+        return self
+
+    def __exit__(self, *exc):
+        ref.ilqrSolver._backward_pass, ref.ilqrSolver._forward_pass, ref.ilqrSolver.solve = self._bp, self._fp, self._solve
+
+
+def trace_arrays(records, J0):
+    """mu per iteration, tried-J table (NaN padded), accepted alpha index (-1: failed search)."""
+    n = len(records)
+    mu = np.array([r["mu"] for r in records])
+    Jt = np.full((n, 10), np.nan)
+    acc = np.full(n, -1, dtype=np.int64)
+    J_star = J0
+    for i, r in enumerate(records):
+        Jt[i, : len(r["J"])] = r["J"]
+        if r["J"][-1] < J_star:
+            acc[i] = len(r["J"]) - 1
+            J_star = r["J"][-1]
+    return mu, Jt, acc
+
+
+# --------------------------------------------------------------------------- #
+# problem construction (mirrors scripts/analysis.py:35-79 and scripts/examples.py)
+# --------------------------------------------------------------------------- #
+def build_problem(models, dt, xf, Q, R, Qf, radius, n_dims, ids):
+    a = len(models)
+    dyn = ref.MultiDynamicalModel([MODEL_CLASSES[m](dt, id_) for m, id_ in zip(models, ids)])
+    s = dyn.x_dims[0]
+    x_dims = [s] * a
+    costs = [
+        ref.ReferenceCost(xf_i, Q[i].copy(), R[i].copy(), Qf[i].copy(), id_)
+        for i, (xf_i, id_) in enumerate(zip(ref.split_agents_gen(xf.flatten(), x_dims), ids))
+    ]
+    prox = ref.ProximityCost(x_dims, radius, list(n_dims))
+    return ref.ilqrProblem(dyn, ref.GameCost(costs, prox))
+
+
+def case_dict(models, dt, N, x0, xf, Q, R, Qf, radius, n_dims, ids, U0, n_lqr_iter, tol):
+    return dict(
+        models=np.array(models), dt=dt, N=N, x0=np.asarray(x0, float).flatten(), xf=np.asarray(xf, float).flatten(),
+        Q=np.stack(Q), R=np.stack(R), Qf=np.stack(Qf), radius=radius, n_dims=np.array(n_dims), ids=np.array(ids),
+        U0=U0, n_lqr_iter=n_lqr_iter, tol=tol,
+    )
+
+
+def run_centralized(name, case, keep_K_steps=(0,)):
+    ref._reset_ids()
+    prob = build_problem(list(case["models"]), case["dt"], case["xf"], case["Q"], case["R"], case["Qf"],
+                         case["radius"], case["n_dims"], list(case["ids"]))
+    solver = ref.ilqrSolver(prob, case["N"])
+    X0, J0 = solver._rollout(case["x0"].reshape(-1, 1), case["U0"])
+    with Trace() as tr:
+        X, U, J = solver.solve(case["x0"].reshape(-1, 1), case["U0"].copy(), n_lqr_iter=int(case["n_lqr_iter"]),
+                               tol=float(case["tol"]), verbose=False)
+    mu, Jt, acc = trace_arrays(tr.records, J0)
+    out = dict(case)
+    out.update(X0=X0, J0=J0, X=X, U=U, J=J, trace_mu=mu, trace_J=Jt, trace_alpha=acc,
+               K_first=tr.records[0]["K"][list(keep_K_steps)], K_first_steps=np.array(keep_K_steps),
+               d_first=tr.records[0]["d"], K_last_iter=tr.records[-1]["K"][list(keep_K_steps)], d_last_iter=tr.records[-1]["d"])
+    np.savez_compressed(os.path.join(OUT, f"solve_{name}.npz"), **out)
+    print(f"solve_{name}: iters={len(mu)} acc={acc.tolist()} J0={J0:.6g} J={J:.6g}")
+    return prob
+
+
+def run_distributed(name, case, Xin, radius_graph, ignore_ids=()):
+    ref._reset_ids()
+    prob = build_problem(list(case["models"]), case["dt"], case["xf"], case["Q"], case["R"], case["Qf"],
+                         case["radius"], case["n_dims"], list(case["ids"]))
+    ids = list(case["ids"])
+    x_dims = prob.game_cost.x_dims
+    graph = ref.define_inter_graph_threshold(Xin, radius_graph, x_dims, ids)
+    with Trace() as tr:
+        X, U, J, info = ref.solve_distributed(prob, Xin, case["U0"].copy(), radius_graph, list(ignore_ids), None, False,
+                                              n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]))
+    # iterations per subproblem, in agent order (solver objects are created in order)
+    order, iters = [], {}
+    for r in tr.records:
+        if r["solver"] not in iters:
+            order.append(r["solver"])
+            iters[r["solver"]] = 0
+        iters[r["solver"]] += 1
+    adj = np.zeros((len(ids), len(ids)), dtype=np.int8)
+    for i, id_ in enumerate(ids):
+        for other in graph[id_]:
+            adj[i, ids.index(int(other))] = 1
+    out = dict(case)
+    out.update(X_in=Xin, radius_graph=radius_graph, ignore_ids=np.array(list(ignore_ids), dtype=np.int64), adjacency=adj,
+               X_dec=X, U_dec=U, J_full=J, sub_iters=np.array([iters[s] for s in order]))
+    np.savez_compressed(os.path.join(OUT, f"dist_{name}.npz"), **out)
+    print(f"dist_{name}: graph sizes={adj.sum(1).tolist()} sub_iters={out['sub_iters'].tolist()} J_full={J:.6g}")
+
+
+def random_case(model, a, seed, energy, n_d, Q, R, Qf, dt=0.1, N=50, radius=0.5, U0=None, n_dims=None,
+                n_lqr_iter=50, tol=1e-3):
+    """random_setup exactly as scripts/analysis.py:45-54 / SURVEY.md section 8d."""
+    ref._reset_ids()
+    np.random.seed(seed)
+    random.seed(seed)
+    s = MODEL_CLASSES[model](dt).n_x
+    c = MODEL_CLASSES[model](dt).n_u
+    x0, xf = ref.random_setup(a, s, is_rotation=False, rel_dist=a, var=a / 2, n_d=n_d, random=True, energy=energy)
+    ids = [100 + i for i in range(a)]
+    if U0 is None:
+        U0 = np.zeros((N, a * c))
+    return case_dict([model] * a, dt, N, x0, xf, [Q] * a, [R] * a, [Qf] * a, radius,
+                     n_dims if n_dims is not None else [n_d] * a, ids, U0, n_lqr_iter, tol)
+
+
+def hover(N, a):
+    return np.tile([0, 0, 0, G * 63 / 2000], (N, a))
+
+
+# --------------------------------------------------------------------------- #
+def gen_dynamics():
+    rng = np.random.default_rng(1234)
+    out = {}
+    for name, cls in MODEL_CLASSES.items():
+        model = cls(0.1)
+        nx, nu = model.n_x, model.n_u
+        xs = rng.normal(size=(16, nx)) * 0.6
+        us = rng.normal(size=(16, nu)) * 0.4
+        if name == "Quadcopter12D":
+            us[:, 3] += G * 63 / 2000
+            us[:, :3] *= 0.01
+        f = np.stack([np.asarray(model.f(x.copy(), u.copy()), dtype=float).flatten() for x, u in zip(xs, us)])
+        xn = np.stack([np.asarray(model(x.copy(), u.copy()), dtype=float).flatten() for x, u in zip(xs, us)])
+        AB = [model.linearize(x.copy(), u.copy()) for x, u in zip(xs, us)]
+        out[f"{name}_x"], out[f"{name}_u"] = xs, us
+        out[f"{name}_f"], out[f"{name}_xn"] = f, xn
+        out[f"{name}_A"] = np.stack([np.asarray(ab[0], dtype=float) for ab in AB])
+        out[f"{name}_B"] = np.stack([np.asarray(ab[1], dtype=float) for ab in AB])
+    # survey-time golden vector, Quad12D
+    x = np.array([.3, -.2, 1.1, .05, -.04, .03, .5, -.3, .2, .1, -.2, .15])
+    u = np.array([.01, -.02, .005, .31])
+    out["survey_quad12_xn"] = ref.integrate(x, u, 0.1, ref.Model.Quadcopter12D)
+    np.savez_compressed(os.path.join(OUT, "dynamics.npz"), **out)
+    print("dynamics.npz written")
+
+
+def gen_cost():
+    """GameCost value + quadraticisation on crowded random points (cost.py:197-239)."""
+    rng = np.random.default_rng(99)
+    out = {}
+    specs = {
+        # name: (models, n_dims, radius)
+        "quad12_3d": (["Quadcopter12D"] * 4, [3] * 4, 0.5),
+        "unicycle_2d": (["Unicycle4D"] * 5, [2] * 5, 0.5),
+        "hetero_q6h6": (["Quadcopter6D", "Quadcopter6D", "Human6D"], [3, 3, 2], 0.3),
+    }
+    for name, (models, n_dims, radius) in specs.items():
+        ref._reset_ids()
+        a = len(models)
+        s = MODEL_CLASSES[models[0]](0.1).n_x
+        c = MODEL_CLASSES[models[0]](0.1).n_u
+        Q = rng.normal(size=(a, s, s))  # deliberately dense and asymmetric (cost.py:60-61)
+        R = rng.normal(size=(a, c, c))
+        Qf = rng.normal(size=(a, s, s))
+        xf = rng.normal(size=a * s)
+        prob = build_problem(models, 0.1, xf, Q, R, Qf, radius, n_dims, [100 + i for i in range(a)])
+        xs = rng.normal(size=(12, a * s)) * 0.25  # crowded: many pairs inside the radius
+        us = rng.normal(size=(12, a * c))
+        gc = prob.game_cost
+        out[f"{name}_Q"], out[f"{name}_R"], out[f"{name}_Qf"], out[f"{name}_xf"] = Q, R, Qf, xf
+        out[f"{name}_x"], out[f"{name}_u"] = xs, us
+        out[f"{name}_models"], out[f"{name}_n_dims"], out[f"{name}_radius"] = np.array(models), np.array(n_dims), radius
+        for term in (False, True):
+            tag = "T" if term else "R"
+            out[f"{name}_L{tag}"] = np.array([np.asarray(gc(x, u, term)).item() for x, u in zip(xs, us)])
+            quads = [gc.quadraticize(x, u, term) for x, u in zip(xs, us)]
+            for k, key in enumerate(["Lx", "Lu", "Lxx", "Luu", "Lux"]):
+                out[f"{name}_{key}{tag}"] = np.stack([np.asarray(q[k], dtype=float) for q in quads])
+    np.savez_compressed(os.path.join(OUT, "cost.npz"), **out)
+    print("cost.npz written")
+
+
+def gen_graphs():
+    """define_inter_graph_threshold (distributed.py:224-247) on random trajectories."""
+    rng = np.random.default_rng(7)
+    out = {}
+    k = 0
+    for a, s, rows in [(2, 4, 1), (5, 4, 51), (10, 12, 51), (15, 12, 51), (7, 6, 1), (4, 6, 7), (12, 12, 23), (6, 3, 100)]:
+        for rep in range(3):
+            X = np.cumsum(rng.normal(size=(rows, a * s)) * 0.15, axis=0) + rng.normal(size=(1, a * s)) * 1.2
+            radius = float(rng.uniform(0.2, 0.9))
+            ids = [100 + i for i in range(a)]
+            graph = ref.define_inter_graph_threshold(X, radius, [s] * a, ids)
+            adj = np.zeros((a, a), dtype=np.int8)
+            for i, id_ in enumerate(ids):
+                for other in graph[id_]:
+                    adj[i, ids.index(int(other))] = 1
+            out[f"g{k}_X"], out[f"g{k}_radius"], out[f"g{k}_s"], out[f"g{k}_adj"] = X, radius, s, adj
+            k += 1
+    out["count"] = k
+    np.savez_compressed(os.path.join(OUT, "graphs.npz"), **out)
+    print(f"graphs.npz written ({k} cases)")
+
+
+def gen_solves():
+    I = np.eye
+    # config 1: 3 x DoubleInt4D centralized (scripts/analysis.py:35-79)
+    c1 = random_case("DoubleInt4D", 3, 0, 10.0, 2, np.diag([1.0, 1, 0, 0]), I(2), 1000 * I(4))
+    run_centralized("cfg1_dint4_a3", c1)
+    # config 2: 5 x Unicycle4D, centralized + DP-iLQR split
+    c2 = random_case("Unicycle4D", 5, 1, 10.0, 2, np.diag([1.0, 1, 0, 0]), I(2), 1000 * I(4))
+    prob = run_centralized("cfg2_uni4_a5", c2)
+    run_distributed("cfg2_uni4_a5_x0", c2, c2["x0"].reshape(1, -1), 0.5)
+    Xroll, _ = ref.ilqrSolver(prob, 50)._rollout(c2["x0"].reshape(-1, 1), c2["U0"])
+    run_distributed("cfg2_uni4_a5_traj", c2, Xroll, 0.5)
+    # crowded unicycles so the graph has real structure
+    c2b = random_case("Unicycle4D", 5, 3, 4.0, 2, np.diag([1.0, 1, 0, 0]), I(2), 1000 * I(4))
+    run_distributed("cfg2_uni4_a5_crowded", c2b, c2b["x0"].reshape(1, -1), 0.5)
+    # config 3: 2 x Quad6D + 1 x Human6D (scripts/examples.py:73-131, scenarios.py:145-152)
+    x0 = np.array([-1.5, 0.1, 1, 0, 0, 0, 1.5, 0, 1, 0, 0, 0, 0, -1, 1.5, 0, 0, 0.0])
+    xf = np.array([1.5, 0, 2, 0, 0, 0, -1.5, 0, 2, 0, 0, 0, 0.0, 2, 1.5, 0, 0, 0])
+    Qq, Rq, Qfq = np.diag([1.0, 1, 1, 5, 5, 5]), np.diag([1.0, 1, 1]), 1e3 * I(6)
+    Qh, Rh = np.diag([1.0, 1, 1, 0, 0, 0]), np.diag([1, 1, 1e-9])
+    U0 = np.c_[np.tile([G, 0, 0], (50, 2)), np.ones((50, 3))]
+    c3 = case_dict(["Quadcopter6D", "Quadcopter6D", "Human6D"], 0.05, 50, x0, xf, [Qq, Qq, Qh], [Rq, Rq, Rh],
+                   [Qfq, Qfq, Qfq], 0.3, [3, 3, 2], [100, 101, 102], U0, 50, 1e-3)
+    run_centralized("cfg3_q6q6h6", c3)
+    run_distributed("cfg3_q6q6h6_x0", c3, x0.reshape(1, -1), 0.3)
+    run_distributed("cfg3_q6q6h6_wide", c3, x0.reshape(1, -1), 1.2)
+    # metric family: a x Quad12D, hover warm start, energy 3a
+    for a, seeds in [(3, (0, 1)), (5, (0,)), (10, (0, 1, 2))]:
+        for seed in seeds:
+            c = random_case("Quadcopter12D", a, seed, 3.0 * a, 3, I(12), I(4), 1000 * I(12), U0=hover(50, a))
+            prob = run_centralized(f"quad12_a{a}_s{seed}", c)
+            if seed == 0:
+                Xh, _ = ref.ilqrSolver(prob, 50)._rollout(c["x0"].reshape(-1, 1), c["U0"])
+                run_distributed(f"quad12_a{a}_s{seed}", c, Xh, 0.5)
+    # config 4: 15 x Quad12D, one decentralised round on the hover rollout
+    c4 = random_case("Quadcopter12D", 15, 0, 45.0, 3, I(12), I(4), 1000 * I(12), U0=hover(50, 15), n_lqr_iter=8)
+    prob = build_problem(list(c4["models"]), 0.1, c4["xf"], c4["Q"], c4["R"], c4["Qf"], 0.5, [3] * 15, list(c4["ids"]))
+    Xh, _ = ref.ilqrSolver(prob, 50)._rollout(c4["x0"].reshape(-1, 1), c4["U0"])
+    run_distributed("cfg4_quad12_a15", c4, Xh, 0.5)
+    # single-agent GameCost problems of every remaining model class
+    for model, Q, R, Qf, dt in [
+        ("Car3D", I(3), I(2), 100 * I(3), 0.05),
+        ("DoubleInt6D", I(6), I(3), 1000 * I(6), 0.05),
+        ("HumanLin6D", I(6), 0.1 * I(3), 1e4 * I(6), 0.05),
+        ("Bike5D", np.diag([1.0, 1, 0, 0, 0]), I(2), 1000 * I(5), 0.05),
+    ]:
+        c = random_case(model, 3, 5, 6.0, 2, Q, R, Qf, dt=dt, N=40)
+        run_centralized(f"misc_{model}_a3", c)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["dynamics", "cost", "graphs", "solves"]
+    if "dynamics" in which:
+        gen_dynamics()
+    if "cost" in which:
+        gen_cost()
+    if "graphs" in which:
+        gen_graphs()
+    if "solves" in which:
+        gen_solves()
