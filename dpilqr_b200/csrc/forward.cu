@@ -1,0 +1,214 @@
+// forward.cu -- Kernel 1: batched rollout + line search (sm_100a).
+//
+// One CTA per problem evaluates EVERY alpha candidate of the line search in one launch:
+//   u_t = U[t] + K[t] (x_t - X[t]) + alpha d[t],  x_{t+1} = RK4(x_t, u_t),  J += cost(x_t, u_t)
+// which replaces the reference's sequential ilqrSolver._rollout / _forward_pass loop
+// (reference control.py:80-114, <=10 passes per iteration) and, per step, the Python loops in
+// MultiDynamicalModel.__call__ (dynamics.py:159-171) and GameCost.__call__ (cost.py:197-206,
+// 79-83, 117-133).
+//
+// Work decomposition inside the CTA, per time step:
+//   gain phase   : warp = 8 gain rows x 4 column lanes; every K[t] element is read from HBM
+//                  exactly once (32-byte sectors fully used) and applied to all candidates from
+//                  registers; 2-stage shuffle reduction.
+//   agent phase  : one thread per (candidate, agent): reference cost, then the RK4 step with the
+//                  state in registers.
+//   pair phase   : one thread per (candidate, agent pair): proximity penalty.
+//   sum phase    : one thread per candidate adds the step cost in the reference's summation
+//                  order (agents ascending; pairs in NumPy pairwise-sum order; cost.py:206).
+#include "cost.cuh"
+#include "kernels.cuh"
+
+namespace dpilqr {
+
+__global__ void __launch_bounds__(256) forward_kernel(const ForwardParams p)
+{
+    extern __shared__ double smem[];
+    const Batch &bt = p.batch;
+    if (p.n_active != nullptr && (int)blockIdx.x >= *p.n_active) return;
+    const int b = p.active ? p.active[blockIdx.x] : blockIdx.x;
+    const int a = bt.n_agents, s = bt.s, c = bt.c, T = bt.horizon;
+    const int n = a * s, m = a * c, pairs = a * (a - 1) / 2;
+    const int NA = p.n_alpha;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+
+    // shared-memory carve-up
+    double *xbuf0 = smem;                 // [NA][n]
+    double *xbuf1 = xbuf0 + NA * n;       // [NA][n]
+    double *dx = xbuf1 + NA * n;          // [NA][n]
+    double *ucur = dx + NA * n;           // [NA][m]
+    double *xref = ucur + NA * m;         // [n]
+    double *uref = xref + n;              // [m]
+    double *dref = uref + m;              // [m]
+    double *refc = dref + m;              // [NA][a]
+    double *proxc = refc + NA * a;        // [NA][max(pairs,1)]
+    double *Jacc = proxc + NA * (pairs > 0 ? pairs : 1);  // [NA]
+
+    const int slot = p.slot ? p.slot[b] : 0;
+    const double *Xb = p.X + (int64_t)b * p.x_stride + (int64_t)slot * p.x_slot_stride;
+    const double *Ub = p.U + (int64_t)b * p.u_stride + (int64_t)slot * p.u_slot_stride;
+    const double *Kb = p.K ? p.K + (int64_t)b * T * m * n : nullptr;
+    const double *db = p.d ? p.d + (int64_t)b * T * m : nullptr;
+    double *Xcb = p.Xc + (int64_t)b * p.xc_stride;
+    double *Ucb = p.Uc + (int64_t)b * p.uc_stride;
+
+    const int32_t *model_b = bt.model + (int64_t)b * a;
+    const int32_t *ndims_b = bt.n_dims + (int64_t)b * a;
+    const int32_t *cidx_b = bt.cost_idx + (int64_t)b * a;
+    const double *xf_b = bt.xf + (int64_t)b * n;
+    const bool has_prox = (a > 1) && (bt.has_prox == nullptr || bt.has_prox[b] != 0);
+    const double radius = has_prox ? bt.radius[b] : 0.0;
+    const double w_ref = bt.weights ? bt.weights[2 * b] : 1.0;
+    const double w_prox = bt.weights ? bt.weights[2 * b + 1] : 200.0;
+    // ProximityCost.__call__ uses the planar distance whenever all n_dims agree (cost.py:122-123)
+    bool uniform_dims = true;
+    for (int i = 1; i < a; ++i) uniform_dims = uniform_dims && (ndims_b[i] == ndims_b[0]);
+
+    for (int k = tid; k < NA * n; k += nthr) xbuf0[k] = Xb[k % n];  // X_next[0] = X[0]
+    if (tid < NA) Jacc[tid] = 0.0;
+    __syncthreads();
+
+    for (int t = 0; t <= T; ++t) {
+        double *xcur = (t & 1) ? xbuf1 : xbuf0;
+        double *xnxt = (t & 1) ? xbuf0 : xbuf1;
+        const bool terminal = (t == T);
+
+        // ---- load reference step, form dx, stream the candidate states out
+        if (!terminal) {
+            if (Kb) {
+                for (int k = tid; k < n; k += nthr) xref[k] = Xb[(int64_t)t * n + k];
+                for (int k = tid; k < m; k += nthr) dref[k] = db[(int64_t)t * m + k];
+            }
+            for (int k = tid; k < m; k += nthr) uref[k] = Ub[(int64_t)t * m + k];
+        }
+        for (int k = tid; k < NA * n; k += nthr) {
+            const int al = k / n, j = k - al * n;
+            Xcb[((int64_t)al * (T + 1) + t) * n + j] = xcur[k];
+        }
+        __syncthreads();
+        if (!terminal) {
+            if (Kb) {
+                for (int k = tid; k < NA * n; k += nthr) dx[k] = xcur[k] - xref[k % n];
+                __syncthreads();
+                // ---- gain phase: u = U[t] + (K[t] dx + alpha d[t])
+                const double *Kt = Kb + (int64_t)t * m * n;
+                const int q = lane & 3, rr = lane >> 2;
+                for (int r0 = warp * 8; r0 < m; r0 += nwarp * 8) {
+                    const int r = r0 + rr;
+                    double acc[kMaxAlpha];
+#pragma unroll
+                    for (int al = 0; al < kMaxAlpha; ++al) acc[al] = 0.0;
+                    if (r < m) {
+                        const double *Krow = Kt + (int64_t)r * n;
+                        for (int j = q; j < n; j += 4) {
+                            const double kv = __ldg(Krow + j);
+#pragma unroll
+                            for (int al = 0; al < kMaxAlpha; ++al)
+                                if (al < NA) acc[al] = fma(kv, dx[al * n + j], acc[al]);
+                        }
+                    }
+#pragma unroll
+                    for (int al = 0; al < kMaxAlpha; ++al) {
+                        if (al < NA) {
+                            double v = acc[al];
+                            v += __shfl_xor_sync(0xffffffffu, v, 1);
+                            v += __shfl_xor_sync(0xffffffffu, v, 2);
+                            if (q == 0 && r < m) ucur[al * m + r] = uref[r] + (v + p.alpha[al] * dref[r]);
+                        }
+                    }
+                }
+            } else {
+                for (int k = tid; k < NA * m; k += nthr) ucur[k] = uref[k % m];
+            }
+            __syncthreads();
+            for (int k = tid; k < NA * m; k += nthr) {
+                const int al = k / m, r = k - al * m;
+                Ucb[((int64_t)al * T + t) * m + r] = ucur[k];
+            }
+        }
+
+        // ---- agent phase: reference cost at (x_t, u_t), then x_{t+1} = RK4(x_t, u_t)
+        for (int item = tid; item < NA * a; item += nthr) {
+            const int al = item / a, i = item - al * a;
+            const int model = model_b[i];
+            const int ci = cidx_b[i];
+            const double *xi = xcur + al * n + i * s;
+            const double *ui = ucur + al * m + i * c;
+            double *xo = xnxt + al * n + i * s;
+            dispatch_model(model, [&]<int M>() {
+                constexpr int NX = model_nx(M), NU = model_nu(M);
+                double x[NX], u[NU];
+#pragma unroll
+                for (int k = 0; k < NX; ++k) x[k] = xi[k];
+#pragma unroll
+                for (int k = 0; k < NU; ++k) u[k] = terminal ? 0.0 : ui[k];
+                const double *Qm = (terminal ? bt.Qf : bt.Q) + (int64_t)ci * NX * NX;
+                const double *Rm = bt.R + (int64_t)ci * NU * NU;
+                refc[al * a + i] = reference_cost<M>(x, u, xf_b + i * s, Qm, Rm, terminal);
+                if (!terminal) {
+                    model_step<M>(bt.dt, x, u);
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) xo[k] = x[k];
+                }
+            });
+        }
+        // ---- pair phase: fmin(0, dist - radius)^2  (reference cost.py:117-133, util.py:48-87)
+        if (has_prox) {
+            for (int item = tid; item < NA * pairs; item += nthr) {
+                const int al = item / pairs, pr = item - al * pairs;
+                // decode pair index -> (i, j), itertools.combinations order
+                int i = 0, rem = pr;
+                while (rem >= a - 1 - i) { rem -= a - 1 - i; ++i; }
+                const int j = i + 1 + rem;
+                const int nd = uniform_dims ? 2 : min(ndims_b[i], ndims_b[j]);
+                proxc[al * pairs + pr] = pair_penalty(xcur + al * n + i * s, xcur + al * n + j * s, nd, radius);
+            }
+        }
+        __syncthreads();
+        // ---- sum phase, reference order: PROX_WEIGHT * prox + REF_WEIGHT * ref_total (cost.py:206)
+        if (tid < NA) {
+            double ref_total = 0.0;
+            for (int i = 0; i < a; ++i) ref_total += refc[tid * a + i];
+            const double prox = has_prox ? numpy_pairwise_sum(proxc + tid * pairs, pairs) : 0.0;
+            Jacc[tid] += w_prox * prox + w_ref * ref_total;
+        }
+        // next iteration's first __syncthreads orders these reads before refc/proxc are rewritten
+    }
+    __syncthreads();
+    if (tid < NA) p.Jc[(int64_t)b * p.jc_stride + tid] = Jacc[tid];
+}
+
+static size_t forward_smem_bytes(int a, int s, int c, int NA)
+{
+    const int n = a * s, m = a * c, pairs = a * (a - 1) / 2;
+    size_t doubles = (size_t)3 * NA * n + (size_t)NA * m + n + 2 * m + (size_t)NA * a + (size_t)NA * (pairs > 0 ? pairs : 1) + NA;
+    return doubles * sizeof(double);
+}
+
+int launch_forward(const ForwardParams &p, int n_blocks, cudaStream_t stream)
+{
+    const Batch &bt = p.batch;
+    if (p.n_alpha < 1 || p.n_alpha > kMaxAlpha) {
+        set_error("n_alpha must be in 1..%d (got %d)", kMaxAlpha, p.n_alpha);
+        return DPILQR_E_INVALID;
+    }
+    if (n_blocks <= 0) return DPILQR_OK;
+    const size_t smem = forward_smem_bytes(bt.n_agents, bt.s, bt.c, p.n_alpha);
+    if (smem > 227 * 1024) {
+        set_error("forward kernel: problem too large for shared memory (%zu bytes)", smem);
+        return DPILQR_E_UNSUPPORTED;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        DPILQR_CUDA(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int items = p.n_alpha * bt.n_agents;
+    const int threads = items <= 128 ? 128 : 256;
+    forward_kernel<<<n_blocks, threads, smem, stream>>>(p);
+    DPILQR_CUDA(cudaGetLastError());
+    return DPILQR_OK;
+}
+
+}  // namespace dpilqr

@@ -1,0 +1,69 @@
+// kernels.cuh -- parameter blocks and host launchers shared by the translation units.
+#pragma once
+#include "common.cuh"
+
+namespace dpilqr {
+
+constexpr int kMaxAlpha = 10;
+
+// Trajectories are addressed as  base + b * stride + slot[b] * slot_stride  so the solver loop can
+// keep every problem's current trajectory inside the ping-pong candidate buffers without copies.
+struct ForwardParams {
+    Batch batch;
+    const double *X;  // current trajectories (only X[:, 0] is read when K == nullptr)
+    const double *U;
+    const double *K;  // may be null (plain rollout)
+    const double *d;
+    double *Xc;       // candidates out
+    double *Uc;
+    double *Jc;
+    int64_t x_stride, u_stride;               // per-problem strides of X / U (doubles)
+    int64_t xc_stride, uc_stride, jc_stride;  // per-problem strides of the candidate outputs
+    int64_t x_slot_stride, u_slot_stride;
+    const int32_t *slot;      // may be null
+    const int32_t *active;    // may be null: compacted list of problem indices
+    const int32_t *n_active;  // may be null: device-side length of `active`
+    int n_alpha;
+    double alpha[kMaxAlpha];
+};
+
+struct LinQuadParams {
+    Batch batch;
+    const double *X;
+    const double *U;
+    double *stage;
+    int32_t *status;
+    int64_t x_stride, u_stride, x_slot_stride, u_slot_stride;
+    const int32_t *slot;
+    const int32_t *active;
+    const int32_t *n_active;
+    int n_blocks_per_problem;
+};
+
+struct BackwardParams {
+    Batch batch;
+    const double *stage;
+    const double *mu;
+    double *K;
+    double *d;
+    int32_t *status;
+    const int32_t *active;
+    const int32_t *n_active;
+    double *scratch;  // global scratch for the big-problem path (2*m*n doubles per CTA)
+    int use_global_scratch;
+};
+
+int launch_forward(const ForwardParams &p, int n_blocks, cudaStream_t stream);
+int launch_linquad(const LinQuadParams &p, int n_problems, cudaStream_t stream);
+int launch_stage_to_dense(const Batch &bt, const double *stage, double *A, double *Bm, double *Lx, double *Lu,
+                          double *Lxx, double *Luu, cudaStream_t stream);
+int launch_backward(const BackwardParams &p, int n_blocks, cudaStream_t stream);
+int64_t backward_scratch_doubles(int n_problems, int a, int s, int c);
+int launch_inter_graph(const double *X, int64_t n_scen, int rows, int a, int s, const double *radius, uint64_t *adj,
+                       cudaStream_t stream);
+int launch_game_cost(const Batch &bt, int64_t rows, const double *X, const double *U, int terminal, double *L,
+                     cudaStream_t stream);
+int launch_dynamics(int mode, int model, double dt, int64_t count, const double *x, const double *u, double *out0,
+                    double *out1, cudaStream_t stream);
+
+}  // namespace dpilqr

@@ -1,0 +1,284 @@
+// models.cuh -- device-side single-agent dynamics library (sm_100a).
+//
+// Each model provides the continuous ODE xdot = f(x, u), the zero-order-hold RK4 step the
+// reference integrates with, and the analytic continuous-time Jacobian entries, which the
+// caller discretises with forward Euler (A = I + dt*dfdx, B = dt*dfdu) exactly as the
+// reference does.  Everything is templated on the model id so state vectors live in
+// registers with fully static indexing.
+//
+// Behaviour follows (not copies) the reference:
+//   ODEs + Jacobians   dpilqr/bbdynamics.cpp:108-711, Bike5D dpilqr/dynamics.py:254-277
+//   RK4, 5 sub-steps   dpilqr/bbdynamics.cpp:39-93  (Bike5D: ONE step, dynamics.py:18-38,74)
+//   Euler Jacobians    dpilqr/bbdynamics.cpp:95-106, dynamics.py:112-114
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dpilqr {
+
+enum ModelId : int {
+    kDoubleInt4D = 0,
+    kDoubleInt6D = 1,
+    kCar3D = 2,
+    kUnicycle4D = 3,
+    kQuad6D = 4,
+    kHuman6D = 5,
+    kHumanLin6D = 6,
+    kQuad12D = 7,
+    kBike5D = 8,
+    kModelCount = 9
+};
+
+__host__ __device__ constexpr int model_nx(int m)
+{
+    return m == kDoubleInt4D ? 4 : m == kDoubleInt6D ? 6 : m == kCar3D ? 3 : m == kUnicycle4D ? 4
+         : m == kQuad6D ? 6 : m == kHuman6D ? 6 : m == kHumanLin6D ? 6 : m == kQuad12D ? 12
+         : m == kBike5D ? 5 : -1;
+}
+__host__ __device__ constexpr int model_nu(int m)
+{
+    return m == kDoubleInt4D ? 2 : m == kDoubleInt6D ? 3 : m == kCar3D ? 2 : m == kUnicycle4D ? 2
+         : m == kQuad6D ? 3 : m == kHuman6D ? 3 : m == kHumanLin6D ? 3 : m == kQuad12D ? 4
+         : m == kBike5D ? 2 : -1;
+}
+
+constexpr double kGravity = 9.80665;
+// Quadcopter12D rigid-body constants: thrust/mass gain, torque/inertia gains and the
+// gyroscopic coupling ratios (I_j - I_k) / I_i of the airframe the reference models.
+constexpr double kThrustGain = 2000.0 / 63.0;
+constexpr double kTauX = 625000000000000000.0 / 10982593196059.0;
+constexpr double kTauY = 5000000000000000000.0 / 92848985528431.0;
+constexpr double kTauZ = 10000000000000000000.0 / 271597947137541.0;
+constexpr double kGyroX = 85899976080679.0 / 175721491136944.0;
+constexpr double kGyroY = 95876456000597.0 / 185697971056862.0;
+constexpr double kGyroZ = 9976479919918.0 / 271597947137541.0;
+
+// ------------------------------------------------------------------------------------------
+// xdot = f(x, u)
+// ------------------------------------------------------------------------------------------
+template <int M>
+__device__ __forceinline__ void model_f(const double (&x)[model_nx(M)], const double (&u)[model_nu(M)],
+                                        double (&xd)[model_nx(M)])
+{
+    if constexpr (M == kDoubleInt4D) {
+        xd[0] = x[2]; xd[1] = x[3]; xd[2] = u[0]; xd[3] = u[1];
+    } else if constexpr (M == kDoubleInt6D) {
+        xd[0] = x[3]; xd[1] = x[4]; xd[2] = x[5]; xd[3] = u[0]; xd[4] = u[1]; xd[5] = u[2];
+    } else if constexpr (M == kCar3D) {
+        double sn, cs;
+        sincos(x[2], &sn, &cs);
+        xd[0] = u[0] * cs; xd[1] = u[0] * sn; xd[2] = u[1];
+    } else if constexpr (M == kUnicycle4D) {
+        double sn, cs;
+        sincos(x[3], &sn, &cs);
+        xd[0] = x[2] * cs; xd[1] = x[2] * sn; xd[2] = u[0]; xd[3] = u[1];
+    } else if constexpr (M == kQuad6D) {
+        xd[0] = x[3]; xd[1] = x[4]; xd[2] = x[5];
+        xd[3] = kGravity * tan(u[2]);
+        xd[4] = -kGravity * tan(u[1]);
+        xd[5] = u[0] - kGravity;
+    } else if constexpr (M == kHuman6D) {
+        // planar unicycle at constant height whose heading is a *control*
+        double sn, cs;
+        sincos(u[0], &sn, &cs);
+        xd[0] = x[3] * cs; xd[1] = x[3] * sn; xd[2] = 0.0; xd[3] = u[1]; xd[4] = 0.0; xd[5] = 0.0;
+    } else if constexpr (M == kHumanLin6D) {
+        xd[0] = x[3]; xd[1] = x[4]; xd[2] = 0.0; xd[3] = u[0]; xd[4] = u[1]; xd[5] = 0.0;
+    } else if constexpr (M == kQuad12D) {
+        // x = [p(3), yaw, pitch, roll, v_body(3), w_body(3)], u = [tau(3), thrust]
+        double sy, cy, sp, cp, sr, cr;
+        sincos(x[3], &sy, &cy);
+        sincos(x[4], &sp, &cp);
+        sincos(x[5], &sr, &cr);
+        const double icp = 1.0 / cp;
+        const double tp = sp * icp;
+        const double v0 = x[6], v1 = x[7], v2 = x[8];
+        const double w0 = x[9], w1 = x[10], w2 = x[11];
+        const double srsp = sr * sp, crsp = cr * sp;
+        xd[0] = v0 * (cy * cp) + v1 * (srsp * cy - sy * cr) + v2 * (sr * sy + crsp * cy);
+        xd[1] = v0 * (sy * cp) + v1 * (srsp * sy + cr * cy) + v2 * (crsp * sy - sr * cy);
+        xd[2] = v1 * (sr * cp) - v0 * sp + v2 * (cr * cp);
+        const double wq = w1 * sr + w2 * cr;
+        xd[3] = wq * icp;
+        xd[4] = w1 * cr - w2 * sr;
+        xd[5] = w0 + wq * tp;
+        xd[6] = v1 * w2 - v2 * w1 + kGravity * sp;
+        xd[7] = v2 * w0 - v0 * w2 - kGravity * (sr * cp);
+        xd[8] = kThrustGain * u[3] + v0 * w1 - v1 * w0 - kGravity * (cr * cp);
+        xd[9] = kTauX * u[0] - kGyroX * (w1 * w2);
+        xd[10] = kTauY * u[1] + kGyroY * (w0 * w2);
+        xd[11] = kTauZ * u[2] - kGyroZ * (w0 * w1);
+    } else if constexpr (M == kBike5D) {
+        double sn, cs;
+        sincos(x[3], &sn, &cs);
+        xd[0] = x[2] * cs; xd[1] = x[2] * sn; xd[2] = u[0]; xd[3] = x[2] * tan(x[4]); xd[4] = u[1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// x <- Phi_dt(x, u): classic RK4 with zero-order-hold controls.
+// ------------------------------------------------------------------------------------------
+template <int M>
+__device__ __forceinline__ void model_step(double dt, double (&x)[model_nx(M)], const double (&u)[model_nu(M)])
+{
+    constexpr int NX = model_nx(M);
+    constexpr int kSub = (M == kBike5D) ? 1 : 5;
+    const double h = (M == kBike5D) ? dt : dt / 5;
+    const double hh = h / 2.0;
+    const double h6 = h / 6.0;
+#pragma unroll 1
+    for (int sub = 0; sub < kSub; ++sub) {
+        double k[NX], acc[NX], xs[NX];
+        model_f<M>(x, u, k);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { acc[i] = k[i]; xs[i] = x[i] + hh * k[i]; }
+        model_f<M>(xs, u, k);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = x[i] + hh * k[i]; }
+        model_f<M>(xs, u, k);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = x[i] + h * k[i]; }
+        model_f<M>(xs, u, k);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] += h6 * (acc[i] + k[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Continuous-time Jacobian entries.  `Sink` receives the structurally non-zero entries through
+// sink.a(row, col, value) / sink.b(row, col, value); everything else is zero.
+// ------------------------------------------------------------------------------------------
+template <int M, class Sink>
+__device__ __forceinline__ void model_jacobian(const double (&x)[model_nx(M)], const double (&u)[model_nu(M)], Sink &sink)
+{
+    if constexpr (M == kDoubleInt4D) {
+        sink.a(0, 2, 1.0); sink.a(1, 3, 1.0);
+        sink.b(2, 0, 1.0); sink.b(3, 1, 1.0);
+    } else if constexpr (M == kDoubleInt6D) {
+        sink.a(0, 3, 1.0); sink.a(1, 4, 1.0); sink.a(2, 5, 1.0);
+        sink.b(3, 0, 1.0); sink.b(4, 1, 1.0); sink.b(5, 2, 1.0);
+    } else if constexpr (M == kCar3D) {
+        double sn, cs;
+        sincos(x[2], &sn, &cs);
+        sink.a(0, 2, -u[0] * sn); sink.a(1, 2, u[0] * cs);
+        sink.b(0, 0, cs); sink.b(1, 0, sn); sink.b(2, 1, 1.0);
+    } else if constexpr (M == kUnicycle4D) {
+        double sn, cs;
+        sincos(x[3], &sn, &cs);
+        sink.a(0, 2, cs); sink.a(0, 3, -x[2] * sn);
+        sink.a(1, 2, sn); sink.a(1, 3, x[2] * cs);
+        sink.b(2, 0, 1.0); sink.b(3, 1, 1.0);
+    } else if constexpr (M == kQuad6D) {
+        const double t1 = tan(u[1]), t2 = tan(u[2]);
+        sink.a(0, 3, 1.0); sink.a(1, 4, 1.0); sink.a(2, 5, 1.0);
+        sink.b(3, 2, kGravity * (t2 * t2) + kGravity);
+        sink.b(4, 1, -kGravity * (t1 * t1) - kGravity);
+        sink.b(5, 0, 1.0);
+    } else if constexpr (M == kHuman6D) {
+        double sn, cs;
+        sincos(u[0], &sn, &cs);
+        sink.a(0, 3, cs); sink.a(1, 3, sn);
+        sink.b(0, 0, -x[3] * sn); sink.b(1, 0, x[3] * cs); sink.b(3, 1, 1.0);
+    } else if constexpr (M == kHumanLin6D) {
+        sink.a(0, 3, 1.0); sink.a(1, 4, 1.0);
+        sink.b(3, 0, 1.0); sink.b(4, 1, 1.0);
+    } else if constexpr (M == kQuad12D) {
+        double sy, cy, sp, cp, sr, cr;
+        sincos(x[3], &sy, &cy);
+        sincos(x[4], &sp, &cp);
+        sincos(x[5], &sr, &cr);
+        const double icp = 1.0 / cp;
+        const double tp = sp * icp;
+        const double sec2 = tp * tp + 1.0;
+        const double v0 = x[6], v1 = x[7], v2 = x[8];
+        const double w0 = x[9], w1 = x[10], w2 = x[11];
+        // rotation matrix body -> world, R = Rz(yaw) Ry(pitch) Rx(roll)
+        const double r00 = cy * cp, r01 = sr * sp * cy - sy * cr, r02 = sr * sy + sp * cr * cy;
+        const double r10 = sy * cp, r11 = sr * sy * sp + cr * cy, r12 = sy * sp * cr - sr * cy;
+        const double r20 = -sp, r21 = sr * cp, r22 = cr * cp;
+        // d(R v)/d yaw = [-row1; row0; 0]
+        sink.a(0, 3, -(v0 * r10 + v1 * r11 + v2 * r12));
+        sink.a(1, 3, v0 * r00 + v1 * r01 + v2 * r02);
+        // d(R v)/d pitch
+        const double q = -v0 * sp + v1 * (sr * cp) + v2 * (cr * cp);
+        sink.a(0, 4, cy * q);
+        sink.a(1, 4, sy * q);
+        sink.a(2, 4, -v0 * cp - v1 * (sr * sp) - v2 * (sp * cr));
+        // d(R v)/d roll
+        sink.a(0, 5, v1 * r02 - v2 * r01);
+        sink.a(1, 5, v1 * r12 - v2 * r11);
+        sink.a(2, 5, v1 * r22 - v2 * r21);
+        // d(R v)/d v = R
+        sink.a(0, 6, r00); sink.a(0, 7, r01); sink.a(0, 8, r02);
+        sink.a(1, 6, r10); sink.a(1, 7, r11); sink.a(1, 8, r12);
+        sink.a(2, 6, r20); sink.a(2, 7, r21); sink.a(2, 8, r22);
+        // Euler-angle kinematics
+        const double wq = w1 * sr + w2 * cr;  // d/d roll of which is wr
+        const double wr = w1 * cr - w2 * sr;
+        sink.a(3, 4, wq * sp * (icp * icp));
+        sink.a(3, 5, wr * icp);
+        sink.a(3, 10, sr * icp);
+        sink.a(3, 11, cr * icp);
+        sink.a(4, 5, -wq);
+        sink.a(4, 10, cr);
+        sink.a(4, 11, -sr);
+        sink.a(5, 4, wq * sec2);
+        sink.a(5, 5, wr * tp);
+        sink.a(5, 9, 1.0);
+        sink.a(5, 10, sr * tp);
+        sink.a(5, 11, cr * tp);
+        // body-frame translational dynamics
+        sink.a(6, 4, kGravity * cp);
+        sink.a(6, 7, w2); sink.a(6, 8, -w1); sink.a(6, 10, -v2); sink.a(6, 11, v1);
+        sink.a(7, 4, kGravity * (sr * sp));
+        sink.a(7, 5, -kGravity * (cr * cp));
+        sink.a(7, 6, -w2); sink.a(7, 8, w0); sink.a(7, 9, v2); sink.a(7, 11, -v0);
+        sink.a(8, 4, kGravity * (sp * cr));
+        sink.a(8, 5, kGravity * (sr * cp));
+        sink.a(8, 6, w1); sink.a(8, 7, -w0); sink.a(8, 9, -v1); sink.a(8, 10, v0);
+        // Euler's rotation equations
+        sink.a(9, 10, -kGyroX * w2); sink.a(9, 11, -kGyroX * w1);
+        sink.a(10, 9, kGyroY * w2); sink.a(10, 11, kGyroY * w0);
+        sink.a(11, 9, -kGyroZ * w1); sink.a(11, 10, -kGyroZ * w0);
+        sink.b(8, 3, kThrustGain);
+        sink.b(9, 0, kTauX); sink.b(10, 1, kTauY); sink.b(11, 2, kTauZ);
+    } else if constexpr (M == kBike5D) {
+        double sn, cs;
+        sincos(x[3], &sn, &cs);
+        const double tf = tan(x[4]);
+        sink.a(0, 2, cs); sink.a(0, 3, -x[2] * sn);
+        sink.a(1, 2, sn); sink.a(1, 3, x[2] * cs);
+        sink.a(3, 2, tf); sink.a(3, 4, x[2] * (tf * tf + 1.0));
+        sink.b(2, 0, 1.0); sink.b(4, 1, 1.0);
+    }
+}
+
+// Sink writing the Euler-discretised dense blocks A (NX x NX) and B (NX x NU), row-major with
+// leading dimensions lda/ldb, into memory the caller has pre-set to A = I, B = 0.
+struct EulerDenseSink {
+    double *A;
+    double *B;
+    int lda, ldb;
+    double dt;
+    __device__ __forceinline__ void a(int r, int c, double v) { A[r * lda + c] = (r == c ? 1.0 : 0.0) + dt * v; }
+    __device__ __forceinline__ void b(int r, int c, double v) { B[r * ldb + c] = dt * v; }
+};
+
+// Runtime dispatch helper: calls fn.template operator()<M>() for the model id.
+template <class Fn>
+__device__ __forceinline__ void dispatch_model(int model, Fn &&fn)
+{
+    switch (model) {
+    case kDoubleInt4D: fn.template operator()<kDoubleInt4D>(); break;
+    case kDoubleInt6D: fn.template operator()<kDoubleInt6D>(); break;
+    case kCar3D: fn.template operator()<kCar3D>(); break;
+    case kUnicycle4D: fn.template operator()<kUnicycle4D>(); break;
+    case kQuad6D: fn.template operator()<kQuad6D>(); break;
+    case kHuman6D: fn.template operator()<kHuman6D>(); break;
+    case kHumanLin6D: fn.template operator()<kHumanLin6D>(); break;
+    case kQuad12D: fn.template operator()<kQuad12D>(); break;
+    case kBike5D: fn.template operator()<kBike5D>(); break;
+    default: break;
+    }
+}
+
+}  // namespace dpilqr

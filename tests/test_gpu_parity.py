@@ -1,0 +1,237 @@
+"""Parity of the CUDA path against the golden fixtures (outputs of the unmodified reference) and
+against the CPU oracle, through the drop-in API and the C ABI.  All tests need a B200."""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import dist_case_names, golden, graph_to_adj, oracle_problem, product_problem, rel_err, solve_case_names
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9  # FP64 parity bar of BASELINE.json's north_star
+
+
+def _tols(name):
+    # Bike5D: 18 chaotic iterations amplify last-bit trig differences (see tests/test_oracle.py)
+    return (1e-4, 1e-7) if "Bike5D" in name else (TOL, TOL)
+
+
+MODELS = ["DoubleInt4D", "DoubleInt6D", "Car3D", "Unicycle4D", "Quadcopter6D", "Human6D", "HumanLin6D", "Quadcopter12D", "Bike5D"]
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_dynamics_vs_reference_golden(name):
+    import dpilqr_b200 as dp
+    from dpilqr_b200.dynamics import _device_eval
+
+    g = golden("dynamics.npz")
+    model = dp.Model[name]
+    x, u = g[f"{name}_x"], g[f"{name}_u"]
+    assert np.allclose(_device_eval("f", model, 0.0, x, u), g[f"{name}_f"], rtol=1e-13, atol=1e-14)
+    assert np.allclose(_device_eval("integrate", model, 0.1, x, u), g[f"{name}_xn"], rtol=1e-12, atol=1e-13)
+    A, B = _device_eval("linearize", model, 0.1, x, u)
+    assert np.allclose(A, g[f"{name}_A"], rtol=1e-13, atol=1e-14)
+    assert np.allclose(B, g[f"{name}_B"], rtol=1e-13, atol=1e-14)
+
+
+def test_bbdynamics_names_and_errors():
+    """The four names of the reference's native module (bbdynamicswrap.pyx:8-164) and their error behaviour."""
+    import dpilqr_b200 as dp
+
+    x = np.array([.3, -.2, 1.1, .05, -.04, .03, .5, -.3, .2, .1, -.2, .15])
+    u = np.array([.01, -.02, .005, .31])
+    want = golden("dynamics.npz")["survey_quad12_xn"]
+    assert np.allclose(dp.integrate(x, u, 0.1, dp.Model.Quadcopter12D), want, rtol=1e-13)
+    assert dp.f(x, u, dp.Model.Quadcopter12D).shape == (12,)
+    A, B = dp.linearize(x, u, 0.1, dp.Model.Quadcopter12D)
+    assert A.shape == (12, 12) and B.shape == (12, 4)
+    with pytest.raises(ValueError):
+        dp.integrate(x, u, 0.1, 7)
+    with pytest.raises(ValueError):
+        dp.integrate(np.zeros((12, 2))[:, 0], u, 0.1, dp.Model.Quadcopter12D)  # non-contiguous
+    model = dp.QuadcopterDynamics12D(0.1)
+    assert np.allclose(model(x, u), want, rtol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["quad12_3d", "unicycle_2d", "hetero_q6h6"])
+def test_game_cost_vs_reference_golden(name):
+    import dpilqr_b200 as dp
+
+    g = golden("cost.npz")
+    models = [str(m) for m in g[f"{name}_models"]]
+    case = dict(models=np.array(models), dt=0.1, xf=g[f"{name}_xf"], Q=g[f"{name}_Q"], R=g[f"{name}_R"], Qf=g[f"{name}_Qf"],
+                radius=g[f"{name}_radius"], n_dims=g[f"{name}_n_dims"], ids=np.arange(100, 100 + len(models)))
+    prob = product_problem(case)
+    gc = prob.game_cost
+    for k, (x, u) in enumerate(zip(g[f"{name}_x"], g[f"{name}_u"])):
+        for term, tag in ((False, "R"), (True, "T")):
+            assert np.isclose(np.asarray(gc(x, u, term)).item(), g[f"{name}_L{tag}"][k], rtol=1e-12)
+            for got, key in zip(gc.quadraticize(x, u, term), ["Lx", "Lu", "Lxx", "Luu", "Lux"]):
+                assert np.allclose(got, g[f"{name}_{key}{tag}"][k], rtol=1e-11, atol=1e-11), (key, tag, k)
+
+
+def test_graphs_bit_exact_vs_reference_golden():
+    import dpilqr_b200 as dp
+
+    g = golden("graphs.npz")
+    for k in range(int(g["count"])):
+        X, s = g[f"g{k}_X"], int(g[f"g{k}_s"])
+        a = X.shape[1] // s
+        ids = [100 + i for i in range(a)]
+        graph = dp.define_inter_graph_threshold(X, float(g[f"g{k}_radius"]), [s] * a, ids)
+        assert np.array_equal(graph_to_adj(graph, ids), g[f"g{k}_adj"]), k
+        assert all(v == sorted(v) for v in graph.values())
+    with pytest.raises(ValueError):
+        dp.define_inter_graph_threshold(np.zeros((3, 4)), 0.5, [4], [0])
+
+
+def test_graph_threshold_is_strict_and_planar():
+    """distance == 2*radius is NOT an edge; only the first two coordinates count (distributed.py:229-242)."""
+    import dpilqr_b200 as dp
+
+    X = np.zeros((1, 12))
+    X[0, 6] = 1.0            # agent 1 at planar distance exactly 1.0
+    X[0, 8] = 50.0           # far away in z: ignored
+    assert dp.define_inter_graph_threshold(X, 0.5, [6, 6], [7, 9]) == {7: [7], 9: [9]}
+    assert dp.define_inter_graph_threshold(X, 0.5000001, [6, 6], [7, 9]) == {7: [7, 9], 9: [7, 9]}
+
+
+@pytest.mark.parametrize("name", solve_case_names())
+def test_rollout_and_first_backward_pass(name):
+    import dpilqr_b200 as dp
+
+    case = golden(f"solve_{name}.npz")
+    solver = dp.ilqrSolver(product_problem(case), int(case["N"]))
+    X0, J0 = solver._rollout(case["x0"], case["U0"])
+    assert rel_err(X0, case["X0"]) < 1e-12
+    assert abs(J0 - case["J0"]) <= 1e-12 * abs(case["J0"])
+    K, d = solver._backward_pass(case["X0"], case["U0"])  # mu = 1.0 after construction
+    assert rel_err(K[case["K_first_steps"]], case["K_first"]) < TOL
+    assert rel_err(d, case["d_first"]) < TOL
+    # one line-search candidate through the hook, against the reference's first tried cost
+    Xn, Un, J = solver._forward_pass(case["X0"], case["U0"], K, d, 1.0)
+    assert abs(J - case["trace_J"][0, 0]) <= TOL * abs(case["trace_J"][0, 0])
+
+
+@pytest.mark.parametrize("name", solve_case_names())
+def test_solve_trace_vs_reference_golden(name):
+    import dpilqr_b200 as dp
+
+    case = golden(f"solve_{name}.npz")
+    tol_J, tol_X = _tols(name)
+    solver = dp.ilqrSolver(product_problem(case), int(case["N"]))
+    X, U, J = solver.solve(case["x0"], case["U0"].copy(), n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]), verbose=False)
+    tr = solver.last_trace
+    assert tr["iters"] == len(case["trace_mu"])                      # same iteration count
+    assert tr["alpha_index"].tolist() == case["trace_alpha"].tolist()  # same accepted step sizes
+    assert np.array_equal(tr["mu"], case["trace_mu"])                # same regularisation schedule
+    for i, k in enumerate(case["trace_alpha"]):
+        tried = slice(0, k + 1) if k >= 0 else slice(0, 10)
+        assert np.allclose(tr["J_tried"][i, tried], case["trace_J"][i, tried], rtol=tol_J), i
+    assert rel_err(X, case["X"]) < tol_X and rel_err(U, case["U"]) < tol_X
+    assert abs(J - case["J"]) <= tol_J * abs(case["J"])
+
+
+@pytest.mark.parametrize("name", dist_case_names())
+def test_solve_distributed_vs_reference_golden(name):
+    import dpilqr_b200 as dp
+
+    case = golden(f"dist_{name}.npz")
+    prob = product_problem(case)
+    ids = [int(v) for v in case["ids"]]
+    results, total = dp.solve_distributed_batch([prob], [case["X_in"]], [case["U0"]], float(case["radius_graph"]),
+                                                [[int(v) for v in case["ignore_ids"]]], n_lqr_iter=int(case["n_lqr_iter"]),
+                                                tol=float(case["tol"]))
+    X, U, J, info = results[0]
+    assert np.array_equal(graph_to_adj({k: v[1] for k, v in info.items()}, ids), case["adjacency"])
+    assert total == int(case["sub_iters"].sum())
+    assert rel_err(X, case["X_dec"]) < TOL and rel_err(U, case["U_dec"]) < TOL
+    assert abs(J - case["J_full"]) <= TOL * abs(case["J_full"])
+    X2, U2, J2, info2 = dp.solve_distributed(prob, case["X_in"], case["U0"], float(case["radius_graph"]), None, None, False,
+                                             n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]))
+    assert np.array_equal(X2, X) and np.array_equal(U2, U) and J2 == J
+
+
+def test_batch_equals_single_bitwise():
+    """Sharding/batching independent problems must not change numerics."""
+    import dpilqr_b200 as dp
+
+    names = ["quad12_a3_s0", "quad12_a3_s1"]
+    cases = [golden(f"solve_{n}.npz") for n in names]
+    specs = [dp.spec_from_problem(product_problem(c)) for c in cases]
+    batch = dp.CompiledBatch(specs * 3, 50)
+    out = batch.solve(np.stack([c["x0"] for c in cases] * 3), np.stack([c["U0"] for c in cases] * 3), trace=True)
+    X = out["X"].cpu().numpy()
+    for k, c in enumerate(cases):
+        single = dp.CompiledBatch([specs[k]], 50).solve(c["x0"][None], c["U0"][None])
+        for rep in range(3):
+            assert np.array_equal(X[k + 2 * rep], single["X"][0].cpu().numpy())
+        assert int(out["iters"][k]) == len(c["trace_mu"])
+    assert out["total_iters"] == 3 * sum(len(c["trace_mu"]) for c in cases)
+
+
+def test_c_abi_host_entry_point():
+    """dpilqr_solve_batch_host through bare ctypes + NumPy (what a non-torch host binds)."""
+    from dpilqr_b200 import _native
+
+    case = golden("solve_cfg1_dint4_a3.npz")
+    lib = _native.lib()
+    a, s, c, T = 3, 4, 2, int(case["N"])
+    B = 2
+    i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+    f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+    model, ndims, cidx = i32(np.zeros((B, a))), i32(np.full((B, a), 2)), i32(np.zeros((B, a)))
+    Q, R, Qf = f64(case["Q"][:1]), f64(case["R"][:1]), f64(case["Qf"][:1])
+    xf, radius = f64(np.tile(case["xf"], (B, 1))), f64(np.full(B, float(case["radius"])))
+    weights, hasprox = f64(np.tile([1.0, 200.0], (B, 1))), i32(np.ones(B))
+    ptr = lambda arr: arr.ctypes.data
+    hb = _native.BatchStruct(B, a, s, c, T, 1, float(case["dt"]), ptr(model), ptr(ndims), ptr(cidx), ptr(Q), ptr(R), ptr(Qf),
+                             ptr(xf), ptr(radius), ptr(weights), ptr(hasprox))
+    opts = _native.SolveOpts(50, 10, 1e-3, 0.0, 0, 1)
+    x0, U0 = f64(np.tile(case["x0"], (B, 1))), f64(np.tile(case["U0"], (B, 1, 1)))
+    X, U = np.empty((B, T + 1, a * s)), np.empty((B, T, a * c))
+    J, Js = np.empty(B), np.empty(B)
+    iters, status = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+    total = lib.dpilqr_solve_batch_host(ctypes.byref(hb), ctypes.byref(opts), ptr(x0), ptr(U0), ptr(X), ptr(U), ptr(J), ptr(Js),
+                                        ptr(iters), ptr(status), None, None, None, 0)
+    assert total == 2 * len(case["trace_mu"]), _native.last_error()
+    for b in range(B):
+        assert rel_err(X[b], case["X"]) < TOL and rel_err(U[b], case["U"]) < TOL
+        assert abs(J[b] - case["J"]) <= TOL * abs(case["J"])
+    prof = _native.get_profile(reset=True)
+    assert prof["backward"][1] == len(case["trace_mu"]) and prof["backward"][0] > 0.0
+    assert lib.dpilqr_release_cache() == 0
+
+
+def test_solve_argument_errors():
+    import dpilqr_b200 as dp
+
+    case = golden("solve_cfg1_dint4_a3.npz")
+    solver = dp.ilqrSolver(product_problem(case), int(case["N"]))
+    with pytest.raises(ValueError):
+        solver.solve(case["x0"], np.zeros((3, 3)), verbose=False)  # control.py:155-156
+
+
+def test_metric_scale_properties():
+    """Size-independent checks on a larger Quad12D batch: duplicated scenarios agree bitwise, accepted costs
+    decrease monotonically, every problem ends for a reason the reference has."""
+    import dpilqr_b200 as dp
+
+    cases = [golden(f"solve_quad12_a10_s{k}.npz") for k in range(3)]
+    specs = [dp.spec_from_problem(product_problem(c)) for c in cases]
+    reps = 32
+    batch = dp.CompiledBatch(specs * reps, 50)
+    out = batch.solve(np.stack([c["x0"] for c in cases] * reps), np.stack([c["U0"] for c in cases] * reps), trace=True)
+    X, iters, status = out["X"].cpu().numpy(), out["iters"].cpu().numpy(), out["status"].cpu().numpy()
+    tj, ta = out["trace_J"].cpu().numpy(), out["trace_alpha"].cpu().numpy()
+    for k, c in enumerate(cases):
+        assert iters[k] == len(c["trace_mu"])
+        assert ta[k, :iters[k]].tolist() == c["trace_alpha"].tolist()
+        assert rel_err(X[k], c["X"]) < TOL
+        for rep in range(1, reps):
+            assert np.array_equal(X[k + 3 * rep], X[k])
+        acc = [tj[k, i, ta[k, i]] for i in range(iters[k]) if ta[k, i] >= 0]
+        assert all(b < a for a, b in zip([c["J0"]] + acc[:-1], acc))
+    assert np.all((status & (16 | 32 | 64)) != 0)
