@@ -78,7 +78,8 @@ EXPORTS = [
     "dpilqr_last_error", "dpilqr_version", "dpilqr_device_count", "dpilqr_model_nx", "dpilqr_model_nu",
     "dpilqr_stage_stride", "dpilqr_workspace_bytes", "dpilqr_f", "dpilqr_integrate", "dpilqr_linearize",
     "dpilqr_rollout_linesearch", "dpilqr_linearize_quadraticize", "dpilqr_game_cost", "dpilqr_stage_to_dense",
-    "dpilqr_backward", "dpilqr_inter_graph", "dpilqr_solve_batch", "dpilqr_solve_batch_host", "dpilqr_get_profile", "dpilqr_release_cache",
+    "dpilqr_backward", "dpilqr_inter_graph", "dpilqr_solve_batch", "dpilqr_solve_batch_host", "dpilqr_get_profile", "dpilqr_debug_backward_timing",
+    "dpilqr_release_cache",
 ]
 
 _lib = None
@@ -121,6 +122,7 @@ def lib():
     L.dpilqr_solve_batch_host.restype = i64
     L.dpilqr_solve_batch_host.argtypes = [bp, op, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
     L.dpilqr_get_profile.argtypes = [ctypes.POINTER(Profile), i32]
+    L.dpilqr_debug_backward_timing.argtypes = [vp]
     L.dpilqr_release_cache.restype = i32
     _lib = L
     return L

@@ -51,7 +51,11 @@ struct BackwardParams {
     const int32_t *n_active;
     double *scratch;  // global scratch for the big-problem path (2*m*n doubles per CTA)
     int use_global_scratch;
+    long long *timing;  // optional: 20 per-phase cycle counters written by CTA 0 (debug aid)
+    int debug_mode;     // timing experiments only (wrong numerics): 1 no pivot search, 2 no elimination, 4 no keys
 };
+extern long long *g_backward_timing;
+extern int g_backward_debug_mode;
 
 int launch_forward(const ForwardParams &p, int n_blocks, cudaStream_t stream);
 int launch_linquad(const LinQuadParams &p, int n_problems, cudaStream_t stream);

@@ -7,6 +7,7 @@
 // (reference control.py:179-211, 227-237) taken per problem by the select kernel.  Finished
 // problems leave a compacted active list; the host only reads back one integer per iteration.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <chrono>
 #include <mutex>
@@ -628,6 +629,14 @@ int dpilqr_get_profile(dpilqr_profile *out, int reset)
     std::lock_guard<std::mutex> guard(g_profile_lock);
     if (out) *out = g_profile;
     if (reset) g_profile = dpilqr_profile{};
+    return 0;
+}
+
+int dpilqr_debug_backward_timing(long long *device_counters)
+{
+    g_backward_timing = device_counters;
+    const char *mode = getenv("DPILQR_DEBUG_BACKWARD_MODE");  // timing experiments only, see kernels.cuh
+    g_backward_debug_mode = (device_counters && mode) ? atoi(mode) : 0;
     return 0;
 }
 

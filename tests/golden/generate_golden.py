@@ -58,7 +58,8 @@ class Trace:
 
         def bp(solver, X, U):
             K, d = trace._bp(solver, X, U)
-            trace.records.append({"solver": trace.n_solves, "mu": solver.μ, "K": K, "d": d, "J": [], "alpha": []})
+            trace.records.append({"solver": trace.n_solves, "mu": solver.μ, "K": K, "d": d, "J": [], "alpha": [],
+                                  "X": X.copy(), "U": U.copy()})
             return K, d
 
         def fp(solver, X, U, K, d, α):
@@ -113,6 +114,15 @@ def case_dict(models, dt, N, x0, xf, Q, R, Qf, radius, n_dims, ids, U0, n_lqr_it
     )
 
 
+def accepted_costs(records, J0):
+    out, J_star = [], J0
+    for r in records:
+        if r["J"][-1] < J_star:
+            J_star = r["J"][-1]
+        out.append(J_star)
+    return np.array(out)
+
+
 def run_centralized(name, case, keep_K_steps=(0,)):
     ref._reset_ids()
     prob = build_problem(list(case["models"]), case["dt"], case["xf"], case["Q"], case["R"], case["Qf"],
@@ -123,12 +133,27 @@ def run_centralized(name, case, keep_K_steps=(0,)):
         X, U, J = solver.solve(case["x0"].reshape(-1, 1), case["U0"].copy(), n_lqr_iter=int(case["n_lqr_iter"]),
                                tol=float(case["tol"]), verbose=False)
     mu, Jt, acc = trace_arrays(tr.records, J0)
+    # Sensitivity of THE REFERENCE ITSELF to a one-ulp-sized input perturbation (x0 * (1 +- 1e-15)): how far the
+    # accepted cost of each iteration and the final trajectory move.  iLQR on the ill-conditioned configs is chaotic
+    # (error x10 per iteration), so this is the yardstick for what any re-implementation can reproduce.
+    signs = np.sign(np.random.default_rng(2024).normal(size=case["x0"].shape))
+    with Trace() as tr2:
+        X2, U2, J2 = solver.solve((case["x0"] * (1 + 1e-15 * signs)).reshape(-1, 1), case["U0"].copy(),
+                                  n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]), verbose=False)
+    Ja, Jb = accepted_costs(tr.records, J0), accepted_costs(tr2.records, J0)
+    k = min(len(Ja), len(Jb))
+    sens_J = np.full(len(Ja), np.inf)
+    sens_J[:k] = np.abs(Ja[:k] - Jb[:k]) / np.abs(Ja[:k])
+    sens_X = float(np.max(np.abs(X - X2)) / np.max(np.abs(X)))
+    sens_U = float(np.max(np.abs(U - U2)) / np.max(np.abs(U)))
     out = dict(case)
     out.update(X0=X0, J0=J0, X=X, U=U, J=J, trace_mu=mu, trace_J=Jt, trace_alpha=acc,
+               iter_X=np.stack([r["X"] for r in tr.records]), iter_U=np.stack([r["U"] for r in tr.records]),
+               sens_J=sens_J, sens_X=sens_X, sens_U=sens_U,
                K_first=tr.records[0]["K"][list(keep_K_steps)], K_first_steps=np.array(keep_K_steps),
                d_first=tr.records[0]["d"], K_last_iter=tr.records[-1]["K"][list(keep_K_steps)], d_last_iter=tr.records[-1]["d"])
     np.savez_compressed(os.path.join(OUT, f"solve_{name}.npz"), **out)
-    print(f"solve_{name}: iters={len(mu)} acc={acc.tolist()} J0={J0:.6g} J={J:.6g}")
+    print(f"solve_{name}: iters={len(mu)} acc={acc.tolist()} J0={J0:.6g} J={J:.6g} sens_X={sens_X:.1e} sens_Jmax={sens_J.max():.1e}")
     return prob
 
 
@@ -153,11 +178,16 @@ def run_distributed(name, case, Xin, radius_graph, ignore_ids=()):
     for i, id_ in enumerate(ids):
         for other in graph[id_]:
             adj[i, ids.index(int(other))] = 1
+    signs = np.sign(np.random.default_rng(2024).normal(size=Xin.shape))
+    X2, U2, J2, _ = ref.solve_distributed(prob, Xin * (1 + 1e-15 * signs), case["U0"].copy(), radius_graph, list(ignore_ids), None,
+                                          False, n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]))
+    sens_X = float(np.max(np.abs(X - X2)) / np.max(np.abs(X)))
+    sens_U = float(np.max(np.abs(U - U2)) / np.max(np.abs(U)))
     out = dict(case)
-    out.update(X_in=Xin, radius_graph=radius_graph, ignore_ids=np.array(list(ignore_ids), dtype=np.int64), adjacency=adj,
+    out.update(sens_X=sens_X, sens_U=sens_U, sens_J=abs(J - J2) / abs(J), X_in=Xin, radius_graph=radius_graph, ignore_ids=np.array(list(ignore_ids), dtype=np.int64), adjacency=adj,
                X_dec=X, U_dec=U, J_full=J, sub_iters=np.array([iters[s] for s in order]))
     np.savez_compressed(os.path.join(OUT, f"dist_{name}.npz"), **out)
-    print(f"dist_{name}: graph sizes={adj.sum(1).tolist()} sub_iters={out['sub_iters'].tolist()} J_full={J:.6g}")
+    print(f"dist_{name}: graph sizes={adj.sum(1).tolist()} sub_iters={out['sub_iters'].tolist()} J_full={J:.6g} sens_X={sens_X:.1e}")
 
 
 def random_case(model, a, seed, energy, n_d, Q, R, Qf, dt=0.1, N=50, radius=0.5, U0=None, n_dims=None,

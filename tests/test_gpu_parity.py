@@ -12,10 +12,18 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-9  # FP64 parity bar of BASELINE.json's north_star
 
+# Cases on which the reference iteration is well conditioned: the bar is 1e-9, full stop.
+STRICT = ("quad12_", "cfg1_", "misc_DoubleInt6D", "misc_HumanLin6D", "cfg4_", "cfg2_uni4_a5_x0", "cfg2_uni4_a5_traj",
+          "cfg3_q6q6h6_x0")
 
-def _tols(name):
-    # Bike5D: 18 chaotic iterations amplify last-bit trig differences (see tests/test_oracle.py)
-    return (1e-4, 1e-7) if "Bike5D" in name else (TOL, TOL)
+
+def _tol(name, sens):
+    """1e-9 on the well-conditioned cases.  The remaining golden cases are chaotic *in the reference itself*: the
+    fixtures record how far the reference's own result moves when x0 is perturbed by 1e-15 relative (`sens_*`,
+    tests/golden/generate_golden.py); there the bar is 100x that sensitivity, and never looser than it needs to be."""
+    if name.startswith(STRICT):
+        return TOL
+    return max(TOL, 100.0 * float(sens))
 
 
 MODELS = ["DoubleInt4D", "DoubleInt6D", "Car3D", "Unicycle4D", "Quadcopter6D", "Human6D", "HumanLin6D", "Quadcopter12D", "Bike5D"]
@@ -117,21 +125,75 @@ def test_rollout_and_first_backward_pass(name):
 
 @pytest.mark.parametrize("name", solve_case_names())
 def test_solve_trace_vs_reference_golden(name):
+    """Whole solve from the same inputs: iteration count, accepted step sizes, regularisation schedule, per-iteration
+    accepted cost, final X / U / J."""
     import dpilqr_b200 as dp
 
     case = golden(f"solve_{name}.npz")
-    tol_J, tol_X = _tols(name)
     solver = dp.ilqrSolver(product_problem(case), int(case["N"]))
     X, U, J = solver.solve(case["x0"], case["U0"].copy(), n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]), verbose=False)
     tr = solver.last_trace
-    assert tr["iters"] == len(case["trace_mu"])                      # same iteration count
-    assert tr["alpha_index"].tolist() == case["trace_alpha"].tolist()  # same accepted step sizes
-    assert np.array_equal(tr["mu"], case["trace_mu"])                # same regularisation schedule
-    for i, k in enumerate(case["trace_alpha"]):
-        tried = slice(0, k + 1) if k >= 0 else slice(0, 10)
-        assert np.allclose(tr["J_tried"][i, tried], case["trace_J"][i, tried], rtol=tol_J), i
-    assert rel_err(X, case["X"]) < tol_X and rel_err(U, case["U"]) < tol_X
-    assert abs(J - case["J"]) <= tol_J * abs(case["J"])
+    n_ref = len(case["trace_mu"])
+    J_star, diverged = float(case["J0"]), False
+    for i in range(n_ref):
+        tol_i = _tol(name, case["sens_J"][i])
+        if tol_i > 1e-3:  # the reference itself is unstable from here on (only cfg2 / Bike5D get here)
+            diverged = True
+            break
+        k = int(case["trace_alpha"][i])
+        assert i < tr["iters"] and int(tr["alpha_index"][i]) == k, i       # same accepted step size
+        assert tr["mu"][i] == case["trace_mu"][i]                             # same regularisation
+        if k >= 0:
+            assert abs(tr["J_tried"][i, k] - case["trace_J"][i, k]) <= tol_i * abs(case["trace_J"][i, k]), i
+            for j in range(k):  # rejected candidates that are not runaway rollouts
+                if case["trace_J"][i, j] < 1.5 * J_star:
+                    assert abs(tr["J_tried"][i, j] - case["trace_J"][i, j]) <= 100 * tol_i * abs(case["trace_J"][i, j]), (i, j)
+            J_star = float(case["trace_J"][i, k])
+    if name.startswith(STRICT):
+        assert not diverged
+    if not diverged:
+        assert tr["iters"] == n_ref                                          # same iteration count
+        assert rel_err(X, case["X"]) < _tol(name, case["sens_X"])
+        assert rel_err(U, case["U"]) < _tol(name, case["sens_U"])
+        assert abs(J - case["J"]) <= _tol(name, case["sens_J"][-1]) * abs(case["J"])
+
+
+@pytest.mark.parametrize("name", solve_case_names())
+def test_every_iteration_from_the_reference_iterate(name):
+    """Teacher-forced parity: each iteration is started from the reference's own iterate (X_i, U_i, mu_i), so the
+    1e-9 bar applies to EVERY iteration of EVERY case, chaotic or not: gains, all candidate costs that matter, the
+    accepted step size and the next iterate."""
+    import dpilqr_b200 as dp
+
+    case = golden(f"solve_{name}.npz")
+    N = int(case["N"])
+    batch = dp.CompiledBatch([dp.spec_from_problem(product_problem(case))], N)
+    n_ref = len(case["trace_mu"])
+    J_star = float(case["J0"])
+    for i in range(n_ref):
+        Xi, Ui = case["iter_X"][i], case["iter_U"][i]
+        stage, _ = batch.linearize_quadraticize(Xi[None], Ui[None])
+        K, d, _ = batch.backward(stage, float(case["trace_mu"][i]))
+        if i == 0:
+            assert rel_err(K[0].cpu().numpy()[case["K_first_steps"]], case["K_first"]) < TOL
+            assert rel_err(d[0].cpu().numpy(), case["d_first"]) < TOL
+        if i == n_ref - 1:
+            assert rel_err(K[0].cpu().numpy()[case["K_first_steps"]], case["K_last_iter"]) < TOL
+            assert rel_err(d[0].cpu().numpy(), case["d_last_iter"]) < TOL
+        Xc, Uc, Jc = batch.forward_pass(Xi[None], Ui[None], K, d)
+        got, ref = Jc[0].cpu().numpy(), case["trace_J"][i]
+        k = int(case["trace_alpha"][i])
+        better = np.nonzero(got < J_star)[0]
+        assert (int(better[0]) if better.size else -1) == k, i             # same accepted step size
+        tried = range(k + 1) if k >= 0 else range(10)
+        for j in tried:
+            if j == k or ref[j] < 1.5 * J_star:                              # skip runaway (rejected) rollouts
+                assert abs(got[j] - ref[j]) <= TOL * abs(ref[j]), (i, j)
+        if k >= 0:
+            J_star = float(ref[k])
+            nxt_X = case["iter_X"][i + 1] if i + 1 < n_ref else case["X"]
+            nxt_U = case["iter_U"][i + 1] if i + 1 < n_ref else case["U"]
+            assert rel_err(Xc[0, k].cpu().numpy(), nxt_X) < TOL and rel_err(Uc[0, k].cpu().numpy(), nxt_U) < TOL, i
 
 
 @pytest.mark.parametrize("name", dist_case_names())
@@ -147,8 +209,8 @@ def test_solve_distributed_vs_reference_golden(name):
     X, U, J, info = results[0]
     assert np.array_equal(graph_to_adj({k: v[1] for k, v in info.items()}, ids), case["adjacency"])
     assert total == int(case["sub_iters"].sum())
-    assert rel_err(X, case["X_dec"]) < TOL and rel_err(U, case["U_dec"]) < TOL
-    assert abs(J - case["J_full"]) <= TOL * abs(case["J_full"])
+    assert rel_err(X, case["X_dec"]) < _tol(name, case["sens_X"]) and rel_err(U, case["U_dec"]) < _tol(name, case["sens_U"])
+    assert abs(J - case["J_full"]) <= _tol(name, case["sens_J"]) * abs(case["J_full"])
     X2, U2, J2, info2 = dp.solve_distributed(prob, case["X_in"], case["U0"], float(case["radius_graph"]), None, None, False,
                                              n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]))
     assert np.array_equal(X2, X) and np.array_equal(U2, U) and J2 == J
