@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdpilqr_b200.so")
+# DPILQR_B200_LIB selects an experimental build (dpilqr_b200.build.build_variant); the default is the in-tree library
+LIB_PATH = os.environ.get("DPILQR_B200_LIB") or os.path.join(_HERE, "lib", "libdpilqr_b200.so")
 
 c_double_p = ctypes.c_void_p  # raw device/host addresses are passed as integers
 c_int32_p = ctypes.c_void_p

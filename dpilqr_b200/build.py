@@ -39,6 +39,27 @@ def _digest():
     return h.hexdigest()
 
 
+def build_variant(name, extra_flags):
+    """Experimental build with extra nvcc flags into lib/variants/<name>.so (accuracy / timing experiments)."""
+    outdir = os.path.join(LIBDIR, "variants")
+    objdir = os.path.join(outdir, "obj_" + name)
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+
+    def one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        res = subprocess.run([nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(res.stdout + res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as pool:
+        objs = list(pool.map(one, SOURCES))
+    out = os.path.join(outdir, name + ".so")
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs, "-lcudart"])
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")

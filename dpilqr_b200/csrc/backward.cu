@@ -133,27 +133,21 @@ __device__ __noinline__ void lu_implicit_pivoting(double *__restrict__ W, unsign
         if (held) wrow[k - 1] = held_mult;
         mydone = mydone || (r == pr);
         const bool live = !mydone;
+#ifdef DPILQR_LU_DIVIDE
+        const double mult = wrow[k] / prow[k];  // accuracy experiment: true division instead of the reciprocal
+        (void)rinv;
+#else
         const double mult = wrow[k] * rinv;
+#endif
         held = live && (q == 0);
         held_mult = mult;
         __syncwarp();  // all four threads of the row have read entry (r, k): the pair loop below may overwrite it
-        // Column k+1 first, by all four threads of the row alike (no divergence): the next pivot search needs its
-        // key and the speculative reciprocal as early as possible.  The pair loop recomputes the same value.
-        if (k + 1 < m) {
-            const double v = live ? fma(-mult, prow[k + 1], wrow[k + 1]) : 0.0;
-            const unsigned long long key = live ? pivot_key(v) : 0ull;
-            const double vr = fast_rcp(v);
-            if (myrow && q == 1) {
-                keybuf[((k + 1) & 1) * 64 + r] = key;
-                rinvbuf[((k + 1) & 1) * 64 + r] = vr;
-            }
-        }
-        // Pair loop.  The thread's own pairs live in registers (static indexing) for the whole factorisation and
-        // are mirrored to shared memory after every update; only the pivot row is loaded, and only the pairs that
-        // still change (j >= jp0), so the shared-memory traffic shrinks with the active sub-matrix.  The pair
-        // holding column k+1 may also rewrite the eliminated entry (r, k) with rounding noise: the multiplier is
-        // stored over it at the next step.
+        // All loads of the step are issued up front: the pivot row's entry in column k+1, and the pivot-row pairs
+        // that still change (j >= jp0) -- the thread's own pairs live in registers (static indexing) for the whole
+        // factorisation and are only mirrored to shared memory, so the traffic shrinks with the active sub-matrix.
         const int jp0 = (k + 1) >> 1;
+        const int knext = (k + 1 < m) ? k + 1 : k;
+        const double pnext = prow[knext], wnext = wrow[knext];
         double2 p2[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
@@ -161,6 +155,19 @@ __device__ __noinline__ void lu_implicit_pivoting(double *__restrict__ W, unsign
             p2[i] = make_double2(0.0, 0.0);
             if (live && j >= jp0 && j < npair) p2[i] = *reinterpret_cast<const double2 *>(prow + 2 * j);
         }
+        // Column k+1 first, by all four threads of the row alike (no divergence): the next pivot search needs its
+        // key and the speculative reciprocal as early as possible.  The pair loop recomputes the same value.
+        {
+            const double v = live ? fma(-mult, pnext, wnext) : 0.0;
+            const unsigned long long key = live ? pivot_key(v) : 0ull;
+            const double vr = fast_rcp(v);
+            if (myrow && q == 1 && k + 1 < m) {
+                keybuf[((k + 1) & 1) * 64 + r] = key;
+                rinvbuf[((k + 1) & 1) * 64 + r] = vr;
+            }
+        }
+        // The pair holding column k+1 may also rewrite the eliminated entry (r, k) with rounding noise: the
+        // multiplier is stored over it at the next step.
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
             wreg[i].x = fma(-mult, p2[i].x, wreg[i].x);
@@ -473,13 +480,14 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 }
             }
             if constexpr (USE_MMA) {
-                // The blocked triangular solves of phase D apply the 8x8 diagonal blocks as explicit inverses on
-                // the tensor path: invert them here, in place.  One thread per (factor, block, column of the inverse).
+                // The blocked forward solve of phase D applies the 8x8 diagonal blocks of the unit lower factor (well
+                // conditioned: |l| <= 1) as explicit inverses on the tensor path: invert them here, in place.  One
+                // thread per (block, column of the inverse).
                 constexpr int M = AT * C, NB = M / 8;
                 named_barrier(1, kSolveThreads);
                 const int which = gt / (NB * 8), bb = (gt / 8) % NB, j = gt & 7;  // which: 0 = L, 1 = U
                 double x[8];
-                const bool busy = gt < 2 * NB * 8;
+                const bool busy = gt < NB * 8;
                 if (busy) {
                     const double *F = (which ? Up : Lp) + (8 * bb) * M + 8 * bb;  // F[c * M + rr] = f(rr, c) of this block
                     if (which == 0) {  // unit lower: solve L x = e_j by forward substitution
@@ -586,6 +594,25 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
 #pragma unroll
                     for (int lvl = 0; lvl < NB; ++lvl) {
                         const int blk = dir ? NB - 1 - lvl : lvl;
+                        if (dir == 1) {
+                            // Upper factor: the diagonal block is substituted through by lanes 0..7 (one right-hand
+                            // side each).  Its explicit inverse would be one more tensor instruction pair, but U carries
+                            // the conditioning of Q_uu and the inverse costs about a digit of accuracy in K.
+                            if (lane < 8) {
+                                double x[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) x[j] = Xc[(size_t)(8 * blk + j) * LDN + lane];
+#pragma unroll
+                                for (int j = 7; j >= 0; --j) {
+                                    x[j] *= rdiag[8 * blk + j];
+#pragma unroll
+                                    for (int j2 = 0; j2 < j; ++j2) x[j2] = fma(-F[(8 * blk + j) * M + 8 * blk + j2], x[j], x[j2]);
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) Xc[(size_t)(8 * blk + j) * LDN + lane] = x[j];
+                            }
+                            __syncwarp();
+                        } else {
                         double d0 = 0.0, d1 = 0.0;
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
@@ -594,6 +621,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                         __syncwarp();
                         *reinterpret_cast<double2 *>(Xc + (size_t)(8 * blk + fr) * LDN + 2 * fc) = make_double2(d0, d1);
                         __syncwarp();
+                        }
 #pragma unroll
                         for (int o = 1; o < NB; ++o) {
                             const int b2 = dir ? blk - o : blk + o;

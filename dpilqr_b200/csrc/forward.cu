@@ -21,7 +21,7 @@
 
 namespace dpilqr {
 
-__global__ void __launch_bounds__(256) forward_kernel(const ForwardParams p)
+__global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
 {
     extern __shared__ double smem[];
     const Batch &bt = p.batch;

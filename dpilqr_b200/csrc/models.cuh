@@ -56,8 +56,8 @@ constexpr double kGyroZ = 9976479919918.0 / 271597947137541.0;
 // xdot = f(x, u)
 // ------------------------------------------------------------------------------------------
 template <int M>
-__device__ __forceinline__ void model_f(const double (&x)[model_nx(M)], const double (&u)[model_nu(M)],
-                                        double (&xd)[model_nx(M)])
+__device__ __forceinline__ void model_f_inline(const double (&x)[model_nx(M)], const double (&u)[model_nu(M)],
+                                               double (&xd)[model_nx(M)])
 {
     if constexpr (M == kDoubleInt4D) {
         xd[0] = x[2]; xd[1] = x[3]; xd[2] = u[0]; xd[3] = u[1];
@@ -112,6 +112,25 @@ __device__ __forceinline__ void model_f(const double (&x)[model_nx(M)], const do
         sincos(x[3], &sn, &cs);
         xd[0] = x[2] * cs; xd[1] = x[2] * sn; xd[2] = u[0]; xd[3] = x[2] * tan(x[4]); xd[4] = u[1];
     }
+}
+
+// The heavy ODEs are kept out of line: RK4 evaluates f twenty times per step, and one shared copy of the
+// trigonometric code keeps the rollout kernel inside the instruction cache.  The light ones inline.
+template <int M>
+__device__ __noinline__ void model_f_outlined(const double (&x)[model_nx(M)], const double (&u)[model_nu(M)],
+                                              double (&xd)[model_nx(M)])
+{
+    model_f_inline<M>(x, u, xd);
+}
+
+template <int M>
+__device__ __forceinline__ void model_f(const double (&x)[model_nx(M)], const double (&u)[model_nu(M)],
+                                        double (&xd)[model_nx(M)])
+{
+    if constexpr (M == kQuad12D || M == kQuad6D || M == kBike5D || M == kUnicycle4D || M == kCar3D || M == kHuman6D)
+        model_f_outlined<M>(x, u, xd);
+    else
+        model_f_inline<M>(x, u, xd);
 }
 
 // ------------------------------------------------------------------------------------------
