@@ -98,7 +98,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_scen = args.cpu_scenarios or max(2 * cores, 16)
+    n_scen = args.cpu_scenarios or max(8 * cores, 64)
     vals = []
     for step in range(args.warmup + args.steps):
         res = cpu_reference_run(n_scen)
@@ -284,7 +284,7 @@ def run_gpu_arm(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            base = cpu_reference_run(args.cpu_scenarios or max(2 * cores, 16))
+            base = cpu_reference_run(args.cpu_scenarios or max(8 * cores, 64))
             base.pop("iterations"), base.pop("seconds")
             line["cpu_baseline"] = base
         print(json.dumps(line))
@@ -299,7 +299,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenarios", type=int, default=4096, help="scenarios per GPU")
-    ap.add_argument("--cpu-scenarios", type=int, default=0, help="sample size of the CPU baseline (default 2 x cores)")
+    ap.add_argument("--cpu-scenarios", type=int, default=0, help="sample size of the CPU baseline (default 8 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
