@@ -21,7 +21,16 @@
 
 namespace dpilqr {
 
-__global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
+// doubles in front of the (16-byte aligned) mbarrier + gain staging area of the dynamic shared memory
+__host__ __device__ inline size_t forward_prefix_doubles(int a, int s, int c, int NA)
+{
+    const int n = a * s, m = a * c, pairs = a * (a - 1) / 2;
+    const size_t doubles = (size_t)3 * NA * n + (size_t)NA * m + n + 2 * m + (size_t)NA * a + (size_t)NA * (pairs > 0 ? pairs : 1) + NA;
+    return (doubles + 1) & ~(size_t)1;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : 1) forward_kernel(const ForwardParams p)
 {
     extern __shared__ double smem[];
     const Batch &bt = p.batch;
@@ -44,6 +53,8 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
     double *refc = dref + m;              // [NA][a]
     double *proxc = refc + NA * a;        // [NA][max(pairs,1)]
     double *Jacc = proxc + NA * (pairs > 0 ? pairs : 1);  // [NA]
+    double *mbar_slot = smem + forward_prefix_doubles(a, s, c, NA);  // [2] mbarrier of the K[t] bulk copies
+    double *Ks = mbar_slot + 2;                                       // [m][n] gains of the current step (only with K)
 
     const int slot = p.slot ? p.slot[b] : 0;
     const double *Xb = p.X + (int64_t)b * p.x_stride + (int64_t)slot * p.x_slot_stride;
@@ -65,10 +76,40 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
     bool uniform_dims = true;
     for (int i = 1; i < a; ++i) uniform_dims = uniform_dims && (ndims_b[i] == ndims_b[0]);
 
+    // optional per-phase cycle counters of CTA 0 / thread 0 (debug aid, see dpilqr_debug_backward_timing)
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long tmark = 0;
+    const bool timing = (p.timing != nullptr) && (blockIdx.x == 0) && (tid == 0);
+    auto tick = [&](int slot) {
+        if (timing) {
+            const long long now = clock64();
+            tacc[slot] += now - tmark;
+            tmark = now;
+        }
+    };
     for (int k = tid; k < NA * n; k += nthr) xbuf0[k] = Xb[k % n];  // X_next[0] = X[0]
     if (tid < NA) Jacc[tid] = 0.0;
     __syncthreads();
 
+    // K[t] (m*n contiguous doubles) is staged into shared memory by one TMA bulk copy per step, issued a step
+    // ahead right after the gain phase has consumed the previous one, so its HBM latency hides behind the RK4.
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_slot);
+    const unsigned k_bytes = (unsigned)(m * n * sizeof(double));
+    auto fetch_gains = [&](int t) {  // thread 0 only, after a __syncthreads()
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(k_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(Ks)), "l"(Kb + (int64_t)t * m * n), "r"(k_bytes), "r"(mbar) : "memory");
+    };
+    if (Kb) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) fetch_gains(0);
+    }
+    if (timing) tmark = clock64();
     for (int t = 0; t <= T; ++t) {
         double *xcur = (t & 1) ? xbuf1 : xbuf0;
         double *xnxt = (t & 1) ? xbuf0 : xbuf1;
@@ -87,12 +128,22 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
             Xcb[((int64_t)al * (T + 1) + t) * n + j] = xcur[k];
         }
         __syncthreads();
+        tick(0);
         if (!terminal) {
             if (Kb) {
                 for (int k = tid; k < NA * n; k += nthr) dx[k] = xcur[k] - xref[k % n];
                 __syncthreads();
                 // ---- gain phase: u = U[t] + (K[t] dx + alpha d[t])
-                const double *Kt = Kb + (int64_t)t * m * n;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "WAIT_GAINS:\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                    "@p bra DONE_GAINS;\n"
+                    "bra WAIT_GAINS;\n"
+                    "DONE_GAINS:\n"
+                    "}\n" ::"r"(mbar), "r"(t & 1) : "memory");
+                const double *Kt = Ks;
                 const int q = lane & 3, rr = lane >> 2;
                 for (int r0 = warp * 8; r0 < m; r0 += nwarp * 8) {
                     const int r = r0 + rr;
@@ -102,7 +153,7 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
                     if (r < m) {
                         const double *Krow = Kt + (int64_t)r * n;
                         for (int j = q; j < n; j += 4) {
-                            const double kv = __ldg(Krow + j);
+                            const double kv = Krow[j];
 #pragma unroll
                             for (int al = 0; al < kMaxAlpha; ++al)
                                 if (al < NA) acc[al] = fma(kv, dx[al * n + j], acc[al]);
@@ -122,10 +173,13 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
                 for (int k = tid; k < NA * m; k += nthr) ucur[k] = uref[k % m];
             }
             __syncthreads();
+            if (Kb && tid == 0 && t + 1 < T) fetch_gains(t + 1);
+            tick(1);
             for (int k = tid; k < NA * m; k += nthr) {
                 const int al = k / m, r = k - al * m;
                 Ucb[((int64_t)al * T + t) * m + r] = ucur[k];
             }
+            tick(2);
         }
 
         // ---- agent phase: reference cost at (x_t, u_t), then x_{t+1} = RK4(x_t, u_t)
@@ -153,6 +207,7 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
                 }
             });
         }
+        tick(3);
         // ---- pair phase: fmin(0, dist - radius)^2  (reference cost.py:117-133, util.py:48-87)
         if (has_prox) {
             for (int item = tid; item < NA * pairs; item += nthr) {
@@ -166,6 +221,7 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
             }
         }
         __syncthreads();
+        tick(4);
         // ---- sum phase, reference order: PROX_WEIGHT * prox + REF_WEIGHT * ref_total (cost.py:206)
         if (tid < NA) {
             double ref_total = 0.0;
@@ -173,40 +229,46 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(const ForwardParams p)
             const double prox = has_prox ? numpy_pairwise_sum(proxc + tid * pairs, pairs) : 0.0;
             Jacc[tid] += w_prox * prox + w_ref * ref_total;
         }
+        tick(5);
         // next iteration's first __syncthreads orders these reads before refc/proxc are rewritten
+    }
+    if (timing) {
+        for (int k = 0; k < 6; ++k) p.timing[24 + k] = tacc[k];
     }
     __syncthreads();
     if (tid < NA) p.Jc[(int64_t)b * p.jc_stride + tid] = Jacc[tid];
 }
 
-static size_t forward_smem_bytes(int a, int s, int c, int NA)
+static size_t forward_smem_bytes(int a, int s, int c, int NA, bool with_gains)
 {
-    const int n = a * s, m = a * c, pairs = a * (a - 1) / 2;
-    size_t doubles = (size_t)3 * NA * n + (size_t)NA * m + n + 2 * m + (size_t)NA * a + (size_t)NA * (pairs > 0 ? pairs : 1) + NA;
+    const size_t doubles = forward_prefix_doubles(a, s, c, NA) + 2 + (with_gains ? (size_t)(a * c) * (a * s) : 0);
     return doubles * sizeof(double);
 }
 
-int launch_forward(const ForwardParams &p, int n_blocks, cudaStream_t stream)
+int launch_forward(const ForwardParams &p_in, int n_blocks, cudaStream_t stream)
 {
+    ForwardParams p = p_in;
+    p.timing = g_backward_timing;
     const Batch &bt = p.batch;
     if (p.n_alpha < 1 || p.n_alpha > kMaxAlpha) {
         set_error("n_alpha must be in 1..%d (got %d)", kMaxAlpha, p.n_alpha);
         return DPILQR_E_INVALID;
     }
     if (n_blocks <= 0) return DPILQR_OK;
-    const size_t smem = forward_smem_bytes(bt.n_agents, bt.s, bt.c, p.n_alpha);
+    const size_t smem = forward_smem_bytes(bt.n_agents, bt.s, bt.c, p.n_alpha, p.K != nullptr);
     if (smem > 227 * 1024) {
         set_error("forward kernel: problem too large for shared memory (%zu bytes)", smem);
         return DPILQR_E_UNSUPPORTED;
     }
     static bool attr_set = false;
     if (!attr_set) {
-        DPILQR_CUDA(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DPILQR_CUDA(cudaFuncSetAttribute(forward_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DPILQR_CUDA(cudaFuncSetAttribute(forward_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int items = p.n_alpha * bt.n_agents;
-    const int threads = items <= 128 ? 128 : 256;
-    forward_kernel<<<n_blocks, threads, smem, stream>>>(p);
+    if (items <= 128) forward_kernel<128><<<n_blocks, 128, smem, stream>>>(p);
+    else forward_kernel<256><<<n_blocks, 256, smem, stream>>>(p);
     DPILQR_CUDA(cudaGetLastError());
     return DPILQR_OK;
 }

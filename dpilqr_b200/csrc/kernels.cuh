@@ -25,6 +25,7 @@ struct ForwardParams {
     const int32_t *n_active;  // may be null: device-side length of `active`
     int n_alpha;
     double alpha[kMaxAlpha];
+    long long *timing;  // optional debug cycle counters (slots 24..29 of the dpilqr_debug_backward_timing buffer)
 };
 
 struct LinQuadParams {

@@ -72,8 +72,8 @@ def test_sharded_dp_ilqr_round_matches_reference(case_name, tmp_path):
     # both ranks hold the same, complete result; their shards partition the agents
     assert np.array_equal(outs[0]["X"], outs[1]["X"]) and np.array_equal(outs[0]["U"], outs[1]["U"])
     assert sorted(outs[0]["owned"].tolist() + outs[1]["owned"].tolist()) == list(range(len(case["ids"])))
-    tol = max(1e-9, 100 * float(case["sens_X"]))
-    assert rel_err(outs[0]["X"], case["X_dec"]) < tol and rel_err(outs[0]["U"], case["U_dec"]) < max(1e-9, 100 * float(case["sens_U"]))
+    tol = max(1e-9, 1000 * float(case["sens_X"]))
+    assert rel_err(outs[0]["X"], case["X_dec"]) < tol and rel_err(outs[0]["U"], case["U_dec"]) < max(1e-9, 1000 * float(case["sens_U"]))
 
 
 def test_shard_bounds_partition():
