@@ -144,6 +144,31 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : 1) forward_kerne
                     "DONE_GAINS:\n"
                     "}\n" ::"r"(mbar), "r"(t & 1) : "memory");
                 const double *Kt = Ks;
+                if ((m & 7) == 0 && (n & 3) == 0) {
+                    // FP64 tensor path: dU (m x NA) = K[t] (m x n) * dx^T (n x NA) in 8x8 tiles, k-steps of 4
+                    // (candidates beyond NA are zero columns).  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4)+{0,1}].
+                    const int fr = lane >> 2, fc = lane & 3;
+                    const int n_tiles = (m >> 3) * ((NA + 7) >> 3);
+                    for (int tile = warp; tile < n_tiles; tile += nwarp) {
+                        const int mt = tile % (m >> 3), nt = tile / (m >> 3);
+                        const double *ap = Kt + (size_t)(8 * mt + fr) * n + fc;
+                        const int al_b = 8 * nt + fr;                 // candidate of this lane's B fragment
+                        const double *bp = dx + (size_t)(al_b < NA ? al_b : 0) * n + fc;
+                        const bool bvalid = al_b < NA;
+                        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: independent chains
+                        for (int ks = 0; ks < (n >> 2); ks += 2) {
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                         : "+d"(c0), "+d"(c1) : "d"(ap[4 * ks]), "d"(bvalid ? bp[4 * ks] : 0.0));
+                            if (ks + 1 < (n >> 2))
+                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                             : "+d"(e0), "+d"(e1) : "d"(ap[4 * ks + 4]), "d"(bvalid ? bp[4 * ks + 4] : 0.0));
+                        }
+                        const int r = 8 * mt + fr;
+                        const int al0 = 8 * nt + 2 * fc;
+                        if (al0 < NA) ucur[al0 * m + r] = uref[r] + ((c0 + e0) + p.alpha[al0] * dref[r]);
+                        if (al0 + 1 < NA) ucur[(al0 + 1) * m + r] = uref[r] + ((c1 + e1) + p.alpha[al0 + 1] * dref[r]);
+                    }
+                } else {
                 const int q = lane & 3, rr = lane >> 2;
                 for (int r0 = warp * 8; r0 < m; r0 += nwarp * 8) {
                     const int r = r0 + rr;
@@ -168,6 +193,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : 1) forward_kerne
                             if (q == 0 && r < m) ucur[al * m + r] = uref[r] + (v + p.alpha[al] * dref[r]);
                         }
                     }
+                }
                 }
             } else {
                 for (int k = tid; k < NA * m; k += nthr) ucur[k] = uref[k % m];

@@ -53,6 +53,46 @@ constexpr double kGyroY = 95876456000597.0 / 185697971056862.0;
 constexpr double kGyroZ = 9976479919918.0 / 271597947137541.0;
 
 // ------------------------------------------------------------------------------------------
+// sin and cos for the ODE right-hand sides.  RK4 calls them sixty times per agent and step, and the library sincos
+// (about 125 instructions with its large-argument machinery) dominated the rollout kernel.  This is the textbook
+// scheme in about 35: two-constant Cody-Waite reduction by pi/2 with FMAs, then the fdlibm minimax polynomials on
+// [-pi/4, pi/4] (error about one ulp).  Arguments beyond 1e5 (runaway line-search candidates) and NaN take the
+// library path.
+// ------------------------------------------------------------------------------------------
+static __device__ __noinline__ void ode_sincos_library(double x, double *sn, double *cs) { sincos(x, sn, cs); }
+
+__device__ __forceinline__ void ode_sincos(double x, double *sn, double *cs)
+{
+    if (!(fabs(x) < 1.0e5)) {  // rare; out of line so the hot path stays compact
+        ode_sincos_library(x, sn, cs);
+        return;
+    }
+    const double kd = rint(x * 6.36619772367581382433e-01);
+    const int k = __double2int_rn(kd);
+    double r = fma(-kd, 1.5707963267948966, x);
+    r = fma(-kd, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    double ss = (k & 1) ? c : s;
+    double cc = (k & 1) ? s : c;
+    if (k & 2) ss = -ss;
+    if ((k + 1) & 2) cc = -cc;
+    *sn = ss;
+    *cs = cc;
+}
+
+// ------------------------------------------------------------------------------------------
 // xdot = f(x, u)
 // ------------------------------------------------------------------------------------------
 template <int M>
@@ -65,11 +105,11 @@ __device__ __forceinline__ void model_f_inline(const double (&x)[model_nx(M)], c
         xd[0] = x[3]; xd[1] = x[4]; xd[2] = x[5]; xd[3] = u[0]; xd[4] = u[1]; xd[5] = u[2];
     } else if constexpr (M == kCar3D) {
         double sn, cs;
-        sincos(x[2], &sn, &cs);
+        ode_sincos(x[2], &sn, &cs);
         xd[0] = u[0] * cs; xd[1] = u[0] * sn; xd[2] = u[1];
     } else if constexpr (M == kUnicycle4D) {
         double sn, cs;
-        sincos(x[3], &sn, &cs);
+        ode_sincos(x[3], &sn, &cs);
         xd[0] = x[2] * cs; xd[1] = x[2] * sn; xd[2] = u[0]; xd[3] = u[1];
     } else if constexpr (M == kQuad6D) {
         xd[0] = x[3]; xd[1] = x[4]; xd[2] = x[5];
@@ -79,16 +119,16 @@ __device__ __forceinline__ void model_f_inline(const double (&x)[model_nx(M)], c
     } else if constexpr (M == kHuman6D) {
         // planar unicycle at constant height whose heading is a *control*
         double sn, cs;
-        sincos(u[0], &sn, &cs);
+        ode_sincos(u[0], &sn, &cs);
         xd[0] = x[3] * cs; xd[1] = x[3] * sn; xd[2] = 0.0; xd[3] = u[1]; xd[4] = 0.0; xd[5] = 0.0;
     } else if constexpr (M == kHumanLin6D) {
         xd[0] = x[3]; xd[1] = x[4]; xd[2] = 0.0; xd[3] = u[0]; xd[4] = u[1]; xd[5] = 0.0;
     } else if constexpr (M == kQuad12D) {
         // x = [p(3), yaw, pitch, roll, v_body(3), w_body(3)], u = [tau(3), thrust]
         double sy, cy, sp, cp, sr, cr;
-        sincos(x[3], &sy, &cy);
-        sincos(x[4], &sp, &cp);
-        sincos(x[5], &sr, &cr);
+        ode_sincos(x[3], &sy, &cy);
+        ode_sincos(x[4], &sp, &cp);
+        ode_sincos(x[5], &sr, &cr);
         const double icp = 1.0 / cp;
         const double tp = sp * icp;
         const double v0 = x[6], v1 = x[7], v2 = x[8];
@@ -109,7 +149,7 @@ __device__ __forceinline__ void model_f_inline(const double (&x)[model_nx(M)], c
         xd[11] = kTauZ * u[2] - kGyroZ * (w0 * w1);
     } else if constexpr (M == kBike5D) {
         double sn, cs;
-        sincos(x[3], &sn, &cs);
+        ode_sincos(x[3], &sn, &cs);
         xd[0] = x[2] * cs; xd[1] = x[2] * sn; xd[2] = u[0]; xd[3] = x[2] * tan(x[4]); xd[4] = u[1];
     }
 }
