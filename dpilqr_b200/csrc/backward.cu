@@ -63,124 +63,149 @@ __device__ __forceinline__ double fast_rcp(double v)
 }
 
 // Phase C of the backward kernel: LU factorisation of the m x m matrix W (row-major, W[r*ldw + c]) with partial
-// pivoting, by the kSolveThreads threads of warp group 1.  Four threads per row, each owning every fourth pair of
-// columns (double2 accesses), everything in shared memory, ONE named barrier per column.  While eliminating
-// column k the thread that owns the entry of column k+1 publishes its pivot-search key together with its
-// reciprocal (computed speculatively, off the critical path).  After the barrier each warp finds the arg-max on
-// its own with warp reductions and picks the matching reciprocal up (LAPACK dgetf2 also scales by the reciprocal
-// pivot).  Rows never move: a used pivot row is simply marked (key 0) and its index recorded in order[k].  On
-// return W holds the multipliers l(r, k) in the eliminated positions and the rows of U in the pivot rows.
-// The body of the column loop is branch-free straight-line code (a lone warp per scheduler pays the full branch
-// latency), the loop itself is not unrolled (instruction-cache footprint); kept out of line for a register
-// allocation of its own.  MT > 0 fixes m at compile time.
+// pivoting (the rule of LAPACK dgetf2, which also scales by the reciprocal pivot), by the kSolveThreads threads of
+// warp group 1, with LOOK-AHEAD PIVOTING: the pivot search never sits on the elimination's critical path.
+//
+//   * Row threads (warps 0..6): TPR threads per row, each owning every TPR-th pair of columns.  The pairs live in
+//     registers (static indexing) for the whole factorisation and are mirrored to shared memory after every
+//     update; only the pivot row is loaded, and only the pairs that still change.  In round k they eliminate
+//     column k-1 and then publish the row's entries of columns k and k+1 into a small side buffer.
+//   * The search warp (warp 7) works one column ahead on the side buffer alone: in round k it applies the
+//     elimination of column k-1 to column k itself (same operands, same operations => the same bits the row threads
+//     produce), takes the arg-max of |.| over the unused rows with warp reductions, and publishes the pivot row of
+//     column k together with the reciprocal pivot.
+//   * One named barrier per round.  Rows never move: a used pivot row is simply marked, its index goes to order[k].
+//
+// On return W holds the multipliers l(r, k) in the eliminated positions and the rows of U in the pivot rows.
+// Straight-line round body (a lone warp per scheduler pays the full branch latency), rounds not unrolled
+// (instruction-cache footprint), out of line for a register allocation of its own.  MT > 0 fixes m at compile time.
 template <int MT>
-__device__ __noinline__ void lu_implicit_pivoting(double *__restrict__ W, unsigned long long *__restrict__ keybuf,
-                                                 double *__restrict__ rinvbuf, int *__restrict__ order, int m_rt, int gt)
+__device__ __noinline__ void lu_lookahead(double *__restrict__ W, double *__restrict__ colbuf, double *__restrict__ rinvbuf,
+                                          int *__restrict__ prbuf, int *__restrict__ order, int m_rt, int gt)
 {
     const int m = MT > 0 ? MT : m_rt;
     const int ldw = backward_ldw(m);
     const int npair = (m + 1) >> 1;
-    constexpr int NP = MT > 0 ? ((MT + 1) / 2 + 3) / 4 : 8;  // column pairs per thread
+    const int tpr = (m <= 56) ? 4 : 3;                       // threads per row: rows must fit in warps 0..6
+    constexpr int NP = MT > 0 ? ((MT + 1) / 2 + (MT <= 56 ? 3 : 2)) / (MT <= 56 ? 4 : 3) : 11;  // pairs per thread
     const int lane = gt & 31;
-    const int r = gt >> 2, q = gt & 3;
-    const bool myrow = r < m;
-    double *wrow = W + (myrow ? r : m - 1) * ldw;
     // |v| of a double orders like its bit pattern; +1 so that a live zero still beats a used row (key 0)
     auto pivot_key = [](double v) -> unsigned long long {
         const double av = fabs(v);
         return (av == av) ? (unsigned long long)__double_as_longlong(av) + 1ull : 1ull;
     };
-    if (gt < 128) keybuf[gt] = 0ull;  // rows >= m never compete
-    named_barrier(1, kSolveThreads);
-    if (q == 0 && myrow) {
-        const double v = wrow[0];
-        keybuf[r] = pivot_key(v);
-        rinvbuf[r] = fast_rcp(v);
+    if ((gt >> 5) == 7) {
+        // ------------------------------------------------------------------ search warp
+        const int r0 = lane, r1 = lane + 32;
+        const bool has0 = r0 < m, has1 = r1 < m;
+        bool done0 = !has0, done1 = !has1;
+        int pr_prev = 0;
+        double rinv_prev = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < m; ++k) {
+            double v0, v1;
+            if (k == 0) {
+                v0 = has0 ? W[r0 * ldw] : 0.0;
+                v1 = has1 ? W[r1 * ldw] : 0.0;
+            } else {
+                const double *cb = colbuf + ((k - 1) & 1) * 128;  // [0..63]: column k-1, [64..127]: column k
+                const double pcur = cb[64 + pr_prev];
+                const double a0 = has0 ? cb[r0] : 0.0, b0 = has0 ? cb[64 + r0] : 0.0;
+                const double a1 = has1 ? cb[r1] : 0.0, b1 = has1 ? cb[64 + r1] : 0.0;
+                v0 = fma(-(a0 * rinv_prev), pcur, b0);
+                v1 = fma(-(a1 * rinv_prev), pcur, b1);
+            }
+            const unsigned long long key0 = done0 ? 0ull : pivot_key(v0);
+            const unsigned long long key1 = done1 ? 0ull : pivot_key(v1);
+            const bool second = key1 > key0;
+            const unsigned long long kmax = second ? key1 : key0;
+            const int rsel = second ? r1 : r0;
+            const double vsel = second ? v1 : v0;
+            const unsigned hi = (unsigned)(kmax >> 32);
+            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+            bool mine = (hi == mhi);
+            unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (__popc(bal) > 1) {  // rare: several rows share the top 32 bits
+                const unsigned lo = mine ? (unsigned)kmax : 0u;
+                const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+                mine = mine && (lo == mlo);
+                bal = __ballot_sync(0xffffffffu, mine);
+            }
+            const int win = __ffs(bal) - 1;
+            const int pr = __shfl_sync(0xffffffffu, rsel, win);
+            const double pivot = __shfl_sync(0xffffffffu, vsel, win);
+            const double rinv = fast_rcp(pivot);
+            if (lane == 0) {
+                prbuf[k & 1] = pr;
+                rinvbuf[k & 1] = rinv;
+                order[k] = pr;
+            }
+            done0 = done0 || (r0 == pr);
+            done1 = done1 || (r1 == pr);
+            pr_prev = pr;
+            rinv_prev = rinv;
+            named_barrier(1, kSolveThreads);
+        }
+        named_barrier(1, kSolveThreads);
+        return;
     }
-    named_barrier(1, kSolveThreads);
+    // ---------------------------------------------------------------------- row threads
+    const int r = gt / tpr, q = gt - r * tpr;
+    const bool myrow = r < m;
+    double *wrow = W + (myrow ? r : m - 1) * ldw;
     bool mydone = !myrow;
     double2 wreg[NP];  // this thread's column pairs of row r
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        const int j = q + 4 * i;
+        const int j = q + tpr * i;
         wreg[i] = (j < npair) ? *reinterpret_cast<const double2 *>(wrow + 2 * j) : make_double2(0.0, 0.0);
     }
-    double held_mult = 0.0;  // multiplier of the previous step, stored one barrier later
+    double held_mult = 0.0;  // multiplier of the previous elimination, stored one barrier later
     bool held = false;
 #pragma unroll 1
     for (int k = 0; k < m; ++k) {
-        const unsigned long long *cur = keybuf + (k & 1) * 64;
-        const unsigned long long key0 = cur[lane];
-        const unsigned long long key1 = cur[lane + 32];
-        const unsigned long long kmax = key1 > key0 ? key1 : key0;
-        const int rsel = key1 > key0 ? lane + 32 : lane;
-        const unsigned hi = (unsigned)(kmax >> 32);
-        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-        bool mine = (hi == mhi);
-        unsigned bal = __ballot_sync(0xffffffffu, mine);
-        if (__popc(bal) > 1) {  // rare: several rows share the top 32 bits
-            const unsigned lo = mine ? (unsigned)kmax : 0u;
-            const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
-            mine = mine && (lo == mlo);
-            bal = __ballot_sync(0xffffffffu, mine);
-        }
-        const int pr = __shfl_sync(0xffffffffu, rsel, __ffs(bal) - 1);
-        const double rinv = rinvbuf[(k & 1) * 64 + pr];
-        const double *prow = W + pr * ldw;
-        if (gt == 0) order[k] = pr;
-        // The multiplier of step k-1 replaces the eliminated entry (r, k-1) only now: every thread of the row has
-        // read that entry before the barrier that ended step k-1.
-        if (held) wrow[k - 1] = held_mult;
-        mydone = mydone || (r == pr);
-        const bool live = !mydone;
-#ifdef DPILQR_LU_DIVIDE
-        const double mult = wrow[k] / prow[k];  // accuracy experiment: true division instead of the reciprocal
-        (void)rinv;
-#else
-        const double mult = wrow[k] * rinv;
-#endif
-        held = live && (q == 0);
-        held_mult = mult;
-        __syncwarp();  // all four threads of the row have read entry (r, k): the pair loop below may overwrite it
-        // All loads of the step are issued up front: the pivot row's entry in column k+1, and the pivot-row pairs
-        // that still change (j >= jp0) -- the thread's own pairs live in registers (static indexing) for the whole
-        // factorisation and are only mirrored to shared memory, so the traffic shrinks with the active sub-matrix.
-        const int jp0 = (k + 1) >> 1;
-        const int knext = (k + 1 < m) ? k + 1 : k;
-        const double pnext = prow[knext], wnext = wrow[knext];
-        double2 p2[NP];
+        if (k >= 1) {
+            const int kk = k - 1;  // column eliminated in this round
+            const int pr = prbuf[kk & 1];
+            const double rinv = rinvbuf[kk & 1];
+            const double *prow = W + pr * ldw;
+            // The multiplier of the previous elimination replaces entry (r, kk-1) only now: every thread of the row
+            // has read that entry before the barrier that ended the previous round.
+            if (held) wrow[kk - 1] = held_mult;
+            mydone = mydone || (r == pr);
+            const bool live = !mydone;
+            const double mult = wrow[kk] * rinv;
+            held = live && (q == 0);
+            held_mult = mult;
+            __syncwarp();  // all threads of the row have read entry (r, kk): the pair loop may overwrite it
+            const int jp0 = (kk + 1) >> 1;
+            double2 p2[NP];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            const int j = q + 4 * i;
-            p2[i] = make_double2(0.0, 0.0);
-            if (live && j >= jp0 && j < npair) p2[i] = *reinterpret_cast<const double2 *>(prow + 2 * j);
-        }
-        // Column k+1 first, by all four threads of the row alike (no divergence): the next pivot search needs its
-        // key and the speculative reciprocal as early as possible.  The pair loop recomputes the same value.
-        {
-            const double v = live ? fma(-mult, pnext, wnext) : 0.0;
-            const unsigned long long key = live ? pivot_key(v) : 0ull;
-            const double vr = fast_rcp(v);
-            if (myrow && q == 1 && k + 1 < m) {
-                keybuf[((k + 1) & 1) * 64 + r] = key;
-                rinvbuf[((k + 1) & 1) * 64 + r] = vr;
+            for (int i = 0; i < NP; ++i) {
+                const int j = q + tpr * i;
+                p2[i] = make_double2(0.0, 0.0);
+                if (live && j >= jp0 && j < npair) p2[i] = *reinterpret_cast<const double2 *>(prow + 2 * j);
+            }
+            // The pair holding column kk+1 may also rewrite the eliminated entry (r, kk) with rounding noise: the
+            // multiplier is stored over it in the next round.
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                wreg[i].x = fma(-mult, p2[i].x, wreg[i].x);
+                wreg[i].y = fma(-mult, p2[i].y, wreg[i].y);
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const int j = q + tpr * i;
+                if (live && j >= jp0 && j < npair) *reinterpret_cast<double2 *>(wrow + 2 * j) = wreg[i];
             }
         }
-        // The pair holding column k+1 may also rewrite the eliminated entry (r, k) with rounding noise: the
-        // multiplier is stored over it at the next step.
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            wreg[i].x = fma(-mult, p2[i].x, wreg[i].x);
-            wreg[i].y = fma(-mult, p2[i].y, wreg[i].y);
-        }
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            const int j = q + 4 * i;
-            if (live && j >= jp0 && j < npair) *reinterpret_cast<double2 *>(wrow + 2 * j) = wreg[i];
-        }
+        // publish this row's entries of columns k and k+1 (state after eliminating the columns < k) for the search
+        __syncwarp();
+        if (myrow && q == 1) colbuf[(k & 1) * 128 + r] = wrow[k];
+        if (myrow && q == 2 && k + 1 < m) colbuf[(k & 1) * 128 + 64 + r] = wrow[k + 1];
         named_barrier(1, kSolveThreads);
     }
-    if (held) wrow[m - 1] = held_mult;
+    if (held) wrow[m - 2] = held_mult;
     named_barrier(1, kSolveThreads);
 }
 
@@ -220,8 +245,8 @@ __host__ __device__ constexpr BackwardSmem backward_smem(int a, int S, int C, bo
     L.dv = off;    off += even_up(m);
     L.zv = off;    off += even_up(m);
     L.order = off; off += even_up(((size_t)m + 1) / 2 + 1);  // m ints
-    L.keys = off;  off += 128;                                 // 2 x 64 pivot-search keys
-    L.rinv = off;  off += 128;                                 // 2 x 64 speculative reciprocals
+    L.keys = off;  off += 256;                                 // look-ahead side buffer of the LU
+    L.rinv = off;  off += 4;                                   // reciprocal pivots + pivot rows of two rounds
     L.tacc = off;  off += 20;                                  // debug cycle counters
     L.mbar = off;  off += 2;                                   // mbarrier of the stage-record bulk copies
     L.mats = off;
@@ -268,8 +293,9 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     double *pvec = smem + SM.pvec, *Qx = smem + SM.Qx, *pq = smem + SM.pq;
     double *Qu = smem + SM.Qu, *dv = smem + SM.dv, *zv = smem + SM.zv;
     int *order = reinterpret_cast<int *>(smem + SM.order);  // [m] physical pivot row of step k
-    unsigned long long *keybuf = reinterpret_cast<unsigned long long *>(smem + SM.keys);  // [2][64] pivot-search keys
-    double *rinvbuf = smem + SM.rinv;  // [2][64] reciprocal of each row's candidate pivot (computed speculatively)
+    double *colbuf = smem + SM.keys;   // [2][2][64] look-ahead side buffer of the LU: two columns of every row
+    double *rinvbuf = smem + SM.rinv;  // [2] reciprocal pivots, [2..3] pivot rows (as ints)
+    int *prbuf = reinterpret_cast<int *>(smem + SM.rinv + 2);
     double *QUX, *KB;  // [m][LDN] each; QUX becomes Y in phase E
     if constexpr (GLOBAL) {
         QUX = p.scratch + (size_t)blockIdx.x * 2 * m * LDN;
@@ -466,7 +492,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         if (tid < kSolveThreads) {
             // ================= group 1: phase C, LU with implicit partial pivoting =================
             const int gt = tid;
-            lu_implicit_pivoting<(AT > 0 ? AT * C : 0)>(W, keybuf, rinvbuf, order, m, gt);
+            lu_lookahead<(AT > 0 ? AT * C : 0)>(W, colbuf, rinvbuf, prbuf, order, m, gt);
             tick(2);
             // pack the factors in pivot order so the substitutions read contiguous memory
             for (int e = gt; e < m * m; e += kSolveThreads) {
