@@ -222,6 +222,12 @@ __host__ __device__ constexpr int backward_ldn(int n)
 
 __host__ __device__ constexpr size_t even_up(size_t v) { return (v + 1) & ~(size_t)1; }
 
+// doubles of global (L2-resident) scratch per CTA when a team is too large for shared memory
+__host__ __device__ constexpr size_t backward_scratch_per_cta(int m, int n)
+{
+    return 2 * (size_t)m * backward_ldn(n) + even_up((size_t)m * backward_ldw(m)) + 2 * even_up((size_t)m * m);
+}
+
 // Shared-memory carve-up in doubles (everything 16-byte aligned).
 __host__ __device__ constexpr BackwardSmem backward_smem(int a, int S, int C, bool mats_in_smem)
 {
@@ -231,9 +237,10 @@ __host__ __device__ constexpr BackwardSmem backward_smem(int a, int S, int C, bo
     size_t off = 0;
     L.Pb = off;    off += even_up(nblk * (S * S + 2));
     L.QUU = off;   off += even_up((size_t)m * (m + 4));
-    L.W = off;     off += even_up((size_t)m * backward_ldw(m));
-    L.Lp = off;    off += even_up((size_t)m * m);
-    L.Up = off;    off += even_up((size_t)m * m);
+    // the LU work matrix and the packed factors move to the global scratch together with Q_ux / K for big teams
+    L.W = off;     if (mats_in_smem) off += even_up((size_t)m * backward_ldw(m));
+    L.Lp = off;    if (mats_in_smem) off += even_up((size_t)m * m);
+    L.Up = off;    if (mats_in_smem) off += even_up((size_t)m * m);
     L.rdiag = off; off += even_up(m);
     L.sA = off;    off += even_up((size_t)a * (S * S + 2));
     L.sB = off;    off += even_up((size_t)a * (S * C + 2));
@@ -298,8 +305,12 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     int *prbuf = reinterpret_cast<int *>(smem + SM.rinv + 2);
     double *QUX, *KB;  // [m][LDN] each; QUX becomes Y in phase E
     if constexpr (GLOBAL) {
-        QUX = p.scratch + (size_t)blockIdx.x * 2 * m * LDN;
+        double *base = p.scratch + (size_t)blockIdx.x * backward_scratch_per_cta(m, n);
+        QUX = base;
         KB = QUX + (size_t)m * LDN;
+        W = KB + (size_t)m * LDN;
+        Lp = W + even_up((size_t)m * LDW);
+        Up = Lp + even_up((size_t)m * m);
     } else {
         QUX = smem + SM.mats;
         KB = QUX + (size_t)m * LDN;
@@ -856,7 +867,7 @@ static BackwardPlan plan_backward(int a, int s, int c)
 int64_t backward_scratch_doubles(int n_problems, int a, int s, int c)
 {
     const BackwardPlan plan = plan_backward(a, s, c);
-    return plan.use_global_scratch ? (int64_t)n_problems * 2 * (a * c) * backward_ldn(a * s) : 0;
+    return plan.use_global_scratch ? (int64_t)n_problems * (int64_t)backward_scratch_per_cta(a * c, a * s) : 0;
 }
 
 template <int S, int C, int AT, bool GLOBAL>

@@ -150,12 +150,14 @@ def solve_centralized(solver, xi, U, ids, verbose, **kwargs):
 
 
 def solve_rhc(problem, x0, N, *args, centralized=True, n_d=2, step_size=1, J_converge=None, dist_converge=None,
-              t_diverge=None, i_trial=None, verbose=False, U0=None, **kwargs):
+              t_diverge=None, i_trial=None, verbose=False, U0=None, sharded=False, **kwargs):
     """Receding-horizon loop, centralized or decentralized (reference distributed.py:106-221).
 
     ``U0`` (not in the reference) overrides the ``np.random.rand(N, n_u) * 0.01`` warm start the
     reference draws from the global NumPy RNG (:152); when it is None the same draw is made so a
-    seeded run consumes the RNG identically."""
+    seeded run consumes the RNG identically.  ``sharded=True`` (decentralized mode, under torch.distributed): every
+    rank runs this same loop, solves only its own agents' sub-problems each round, and the ranks exchange the new
+    agent trajectories with one NCCL all-gather per round (dpilqr_b200.parallel)."""
     if (J_converge is None) == (dist_converge is None):
         raise ValueError("Must either specify a convergence cost or distance")
     xf = problem.game_cost.xf
@@ -191,6 +193,13 @@ def solve_rhc(problem, x0, N, *args, centralized=True, n_d=2, step_size=1, J_con
             print(f"t: {t:.3g}")
         if centralized:
             X, U, J, solve_info = solve_centralized(centralized_solver, xi, U, ids, False, **kwargs)
+        elif sharded:
+            from .parallel import solve_distributed_sharded
+
+            t0 = pc()
+            X, U, graph = solve_distributed_sharded(problem, X, U, args[0], args[1] if len(args) > 1 else None, **kwargs)
+            _, J = centralized_solver._rollout(xi, U)
+            solve_info = {id_: (pc() - t0, members) for id_, members in graph.items()}
         else:
             X, U, J, solve_info = solve_distributed(problem, X, U, *args, verbose=False, **kwargs)
         xi = X[step_size]
