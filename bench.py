@@ -158,6 +158,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one backward launch over 3313 problems (profiles/r01_backward_ncu_full.txt)
+NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM = (3.502195e9 + 6.417257e9) / 3313
+
+
 def measure_fp64_peak():
     exe = os.path.join(ROOT, "tools", "bin", "fp64_peak")
     if not os.path.exists(exe):
@@ -165,7 +169,7 @@ def measure_fp64_peak():
     try:
         out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
         vals = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
-        return max(v["tflops"] for v in vals if v.get("kernel") == "dfma")
+        return max(v["tflops"] for v in vals if str(v.get("kernel", "")).startswith(("dfma", "dmma")))
     except Exception:
         return None
 
@@ -251,7 +255,8 @@ def run_gpu_arm(args):
         e2e_value = iters_e2e / (ms_e2e * 1e-3)
         bms, blaunch, bunits = prof["backward"]
         achieved = backward_flops() * bunits / (bms * 1e-3) * 1e-12 if bms > 0 else None
-        peak, peak_src = (fp64_peak, "FP64 DFMA peak measured on this box by tools/bin/fp64_peak (MEASURED_PEAKS.json has no FP64 entry)") \
+        peak, peak_src = (fp64_peak, "FP64 peak measured on this box by tools/bin/fp64_peak, max of the DFMA and DMMA m8n8k4 loops "
+                                     "(MEASURED_PEAKS.json has no FP64 entry)") \
             if fp64_peak else (37.2, "nominal 148 SM x 64 DFMA/clk x 1.965 GHz (fp64_peak binary missing)")
         hbm_peak = 6453.7
         try:
@@ -273,8 +278,14 @@ def run_gpu_arm(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(sum(v[1] for v in prof.values())),
             "clocks": clocks,
-            "roofline": {"kernel": "backward_kernel<12,4,10>", "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+            "roofline": {"kernel": "backward_kernel<12,4,10>", "bound": "tensor", "bound_detail": "FP64 pipe: mma.sync.m8n8k4.f64 tiles + DFMA",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM * bunits / max(blaunch, 1),
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum = 9.919 GB for a 3313-problem launch "
+                                           "(profiles/r01_backward_ncu_full.txt), scaled to this run's average problems per launch; "
+                                           "algorithmic bytes/problem = %d" % backward_hbm_bytes(),
+                         "peak_source": peak_src,
                          "flops_per_launch_unit": backward_flops(), "launches": blaunch, "avg_launch_ms": bms / max(blaunch, 1),
                          "share_of_step": bms / total_ms if total_ms else None},
             "roofline_hbm": {"kernel": "backward_kernel<12,4,10>", "bound": "hbm",
