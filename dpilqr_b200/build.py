@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdpilqr_b200.so")
 SOURCES = ["solver.cu", "forward.cu", "linquad.cu", "backward.cu", "graph.cu", "dynamics_api.cu", "cost_api.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "models.cuh", "cost.cuh", os.path.join("..", "..", "include", "dpilqr_b200.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "models.cuh", "cost.cuh", "lu.cuh", os.path.join("..", "..", "include", "dpilqr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++20", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -23,6 +23,7 @@
 // -> one CTA per SM); only the stage records stream in and K, d stream out.  Problems too large for
 // shared memory keep Q_ux/Y and K in an L2-resident global scratch instead (same code).
 #include "kernels.cuh"
+#include "lu.cuh"
 
 namespace dpilqr {
 
@@ -31,193 +32,23 @@ struct TileSize {
     static constexpr int value = (S % 4 == 0) ? 4 : (S % 3 == 0) ? 3 : S;
 };
 
-constexpr int kSolveThreads = 256;  // warp group 1: LU factorisation; the remaining warps form group 2
-
-__device__ __forceinline__ void named_barrier(int id, int count)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-// D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor path.  Lane l holds A[l/4][l%4], B[l%4][l/4] and
-// D[l/4][2*(l%4) + {0,1}].
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
-// Row stride of the LU work matrix: even (16-byte row alignment for double2 access), at least m + 1, and not a
-// multiple of 16 doubles so that consecutive rows start in different banks.
-__host__ __device__ constexpr int backward_ldw(int m) { return ((m + 2) & ~1) % 16 == 0 ? ((m + 2) & ~1) + 2 : ((m + 2) & ~1); }
-
-// Reciprocal without the special-case branch of __drcp_rn: hardware seed (about 20 bits) plus two Newton steps.
-__device__ __forceinline__ double fast_rcp(double v)
-{
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(v));
-    double e = fma(-v, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-v, x, 1.0);
-    return fma(x, e, x);
-}
-
-// Phase C of the backward kernel: LU factorisation of the m x m matrix W (row-major, W[r*ldw + c]) with partial
-// pivoting (the rule of LAPACK dgetf2, which also scales by the reciprocal pivot), by the kSolveThreads threads of
-// warp group 1, with LOOK-AHEAD PIVOTING: the pivot search never sits on the elimination's critical path.
-//
-//   * Row threads (warps 0..6): TPR threads per row, each owning every TPR-th pair of columns.  The pairs live in
-//     registers (static indexing) for the whole factorisation and are mirrored to shared memory after every
-//     update; only the pivot row is loaded, and only the pairs that still change.  In round k they eliminate
-//     column k-1 and then publish the row's entries of columns k and k+1 into a small side buffer.
-//   * The search warp (warp 7) works one column ahead on the side buffer alone: in round k it applies the
-//     elimination of column k-1 to column k itself (same operands, same operations => the same bits the row threads
-//     produce), takes the arg-max of |.| over the unused rows with warp reductions, and publishes the pivot row of
-//     column k together with the reciprocal pivot.
-//   * One named barrier per round.  Rows never move: a used pivot row is simply marked, its index goes to order[k].
-//
-// On return W holds the multipliers l(r, k) in the eliminated positions and the rows of U in the pivot rows.
-// Straight-line round body (a lone warp per scheduler pays the full branch latency), rounds not unrolled
-// (instruction-cache footprint), out of line for a register allocation of its own.  MT > 0 fixes m at compile time.
-template <int MT>
-__device__ __noinline__ void lu_lookahead(double *__restrict__ W, double *__restrict__ colbuf, double *__restrict__ rinvbuf,
-                                          int *__restrict__ prbuf, int *__restrict__ order, int m_rt, int gt)
-{
-    const int m = MT > 0 ? MT : m_rt;
-    const int ldw = backward_ldw(m);
-    const int npair = (m + 1) >> 1;
-    const int tpr = (m <= 56) ? 4 : 3;                       // threads per row: rows must fit in warps 0..6
-    constexpr int NP = MT > 0 ? ((MT + 1) / 2 + (MT <= 56 ? 3 : 2)) / (MT <= 56 ? 4 : 3) : 11;  // pairs per thread
-    const int lane = gt & 31;
-    // |v| of a double orders like its bit pattern; +1 so that a live zero still beats a used row (key 0)
-    auto pivot_key = [](double v) -> unsigned long long {
-        const double av = fabs(v);
-        return (av == av) ? (unsigned long long)__double_as_longlong(av) + 1ull : 1ull;
-    };
-    if ((gt >> 5) == 7) {
-        // ------------------------------------------------------------------ search warp
-        const int r0 = lane, r1 = lane + 32;
-        const bool has0 = r0 < m, has1 = r1 < m;
-        bool done0 = !has0, done1 = !has1;
-        int pr_prev = 0;
-        double rinv_prev = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < m; ++k) {
-            double v0, v1;
-            if (k == 0) {
-                v0 = has0 ? W[r0 * ldw] : 0.0;
-                v1 = has1 ? W[r1 * ldw] : 0.0;
-            } else {
-                const double *cb = colbuf + ((k - 1) & 1) * 128;  // [0..63]: column k-1, [64..127]: column k
-                const double pcur = cb[64 + pr_prev];
-                const double a0 = has0 ? cb[r0] : 0.0, b0 = has0 ? cb[64 + r0] : 0.0;
-                const double a1 = has1 ? cb[r1] : 0.0, b1 = has1 ? cb[64 + r1] : 0.0;
-                v0 = fma(-(a0 * rinv_prev), pcur, b0);
-                v1 = fma(-(a1 * rinv_prev), pcur, b1);
-            }
-            const unsigned long long key0 = done0 ? 0ull : pivot_key(v0);
-            const unsigned long long key1 = done1 ? 0ull : pivot_key(v1);
-            const bool second = key1 > key0;
-            const unsigned long long kmax = second ? key1 : key0;
-            const int rsel = second ? r1 : r0;
-            const double vsel = second ? v1 : v0;
-            const unsigned hi = (unsigned)(kmax >> 32);
-            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-            bool mine = (hi == mhi);
-            unsigned bal = __ballot_sync(0xffffffffu, mine);
-            if (__popc(bal) > 1) {  // rare: several rows share the top 32 bits
-                const unsigned lo = mine ? (unsigned)kmax : 0u;
-                const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
-                mine = mine && (lo == mlo);
-                bal = __ballot_sync(0xffffffffu, mine);
-            }
-            const int win = __ffs(bal) - 1;
-            const int pr = __shfl_sync(0xffffffffu, rsel, win);
-            const double pivot = __shfl_sync(0xffffffffu, vsel, win);
-            const double rinv = fast_rcp(pivot);
-            if (lane == 0) {
-                prbuf[k & 1] = pr;
-                rinvbuf[k & 1] = rinv;
-                order[k] = pr;
-            }
-            done0 = done0 || (r0 == pr);
-            done1 = done1 || (r1 == pr);
-            pr_prev = pr;
-            rinv_prev = rinv;
-            named_barrier(1, kSolveThreads);
-        }
-        named_barrier(1, kSolveThreads);
-        return;
-    }
-    // ---------------------------------------------------------------------- row threads
-    const int r = gt / tpr, q = gt - r * tpr;
-    const bool myrow = r < m;
-    double *wrow = W + (myrow ? r : m - 1) * ldw;
-    bool mydone = !myrow;
-    double2 wreg[NP];  // this thread's column pairs of row r
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const int j = q + tpr * i;
-        wreg[i] = (j < npair) ? *reinterpret_cast<const double2 *>(wrow + 2 * j) : make_double2(0.0, 0.0);
-    }
-    double held_mult = 0.0;  // multiplier of the previous elimination, stored one barrier later
-    bool held = false;
-#pragma unroll 1
-    for (int k = 0; k < m; ++k) {
-        if (k >= 1) {
-            const int kk = k - 1;  // column eliminated in this round
-            const int pr = prbuf[kk & 1];
-            const double rinv = rinvbuf[kk & 1];
-            const double *prow = W + pr * ldw;
-            // The multiplier of the previous elimination replaces entry (r, kk-1) only now: every thread of the row
-            // has read that entry before the barrier that ended the previous round.
-            if (held) wrow[kk - 1] = held_mult;
-            mydone = mydone || (r == pr);
-            const bool live = !mydone;
-            const double mult = wrow[kk] * rinv;
-            held = live && (q == 0);
-            held_mult = mult;
-            __syncwarp();  // all threads of the row have read entry (r, kk): the pair loop may overwrite it
-            const int jp0 = (kk + 1) >> 1;
-            double2 p2[NP];
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const int j = q + tpr * i;
-                p2[i] = make_double2(0.0, 0.0);
-                if (live && j >= jp0 && j < npair) p2[i] = *reinterpret_cast<const double2 *>(prow + 2 * j);
-            }
-            // The pair holding column kk+1 may also rewrite the eliminated entry (r, kk) with rounding noise: the
-            // multiplier is stored over it in the next round.
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                wreg[i].x = fma(-mult, p2[i].x, wreg[i].x);
-                wreg[i].y = fma(-mult, p2[i].y, wreg[i].y);
-            }
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const int j = q + tpr * i;
-                if (live && j >= jp0 && j < npair) *reinterpret_cast<double2 *>(wrow + 2 * j) = wreg[i];
-            }
-        }
-        // publish this row's entries of columns k and k+1 (state after eliminating the columns < k) for the search
-        __syncwarp();
-        if (myrow && q == 1) colbuf[(k & 1) * 128 + r] = wrow[k];
-        if (myrow && q == 2 && k + 1 < m) colbuf[(k & 1) * 128 + 64 + r] = wrow[k + 1];
-        named_barrier(1, kSolveThreads);
-    }
-    if (held) wrow[m - 2] = held_mult;
-    named_barrier(1, kSolveThreads);
-}
-
 struct BackwardSmem {
     size_t Pb, QUU, W, Lp, Up, rdiag, sA, sB, sL, pvec, Qx, pq, Qu, dv, zv, order, keys, rinv, tacc, mbar, mats, total_doubles;
 };
 
-// Row stride of the Q_ux / K buffers: room for right-hand side n (Q_u) rounded up to a tile of 8, and
-// congruent to 8 modulo 16 doubles so that consecutive rows start 16 banks apart (conflict-free fragments).
+// Row stride of the Q_ux / K buffers: room for right-hand side n (Q_u) rounded up to a tile of 8, and congruent to
+// 4 modulo 16 doubles: the four rows of a tensor-path operand fragment (lane l reads row l%4, column l/4) then start
+// 8 banks apart and a half-warp touches every bank once.
 __host__ __device__ constexpr int backward_ldn(int n)
 {
-    return (((n + 8) & ~7) & 15) == 8 ? ((n + 8) & ~7) : ((n + 8) & ~7) + 8;
+    return (((n + 8) & ~7) & 15) == 0 ? ((n + 8) & ~7) + 4 : ((n + 8) & ~7) + 12;
+}
+
+// Row stride of the packed LU factors, same rule (operand fragments of the blocked substitution)
+__host__ __device__ constexpr int backward_ldf(int m)
+{
+    const int e = (m + 1) & ~1;
+    return (e & 15) == 4 || (e & 15) == 12 ? e : (((e & 15) < 4) ? (e & ~15) + 4 : ((e & 15) < 12) ? (e & ~15) + 12 : (e & ~15) + 20);
 }
 
 __host__ __device__ constexpr size_t even_up(size_t v) { return (v + 1) & ~(size_t)1; }
@@ -225,7 +56,7 @@ __host__ __device__ constexpr size_t even_up(size_t v) { return (v + 1) & ~(size
 // doubles of global (L2-resident) scratch per CTA when a team is too large for shared memory
 __host__ __device__ constexpr size_t backward_scratch_per_cta(int m, int n)
 {
-    return 2 * (size_t)m * backward_ldn(n) + even_up((size_t)m * backward_ldw(m)) + 2 * even_up((size_t)m * m);
+    return 2 * (size_t)m * backward_ldn(n) + even_up((size_t)m * backward_ldw(m)) + 2 * even_up((size_t)m * backward_ldf(m));
 }
 
 // Shared-memory carve-up in doubles (everything 16-byte aligned).
@@ -239,8 +70,8 @@ __host__ __device__ constexpr BackwardSmem backward_smem(int a, int S, int C, bo
     L.QUU = off;   off += even_up((size_t)m * (m + 4));
     // the LU work matrix and the packed factors move to the global scratch together with Q_ux / K for big teams
     L.W = off;     if (mats_in_smem) off += even_up((size_t)m * backward_ldw(m));
-    L.Lp = off;    if (mats_in_smem) off += even_up((size_t)m * m);
-    L.Up = off;    if (mats_in_smem) off += even_up((size_t)m * m);
+    L.Lp = off;    if (mats_in_smem) off += even_up((size_t)m * backward_ldf(m));
+    L.Up = off;    if (mats_in_smem) off += even_up((size_t)m * backward_ldf(m));
     L.rdiag = off; off += even_up(m);
     L.sA = off;    off += even_up((size_t)a * (S * S + 2));
     L.sB = off;    off += even_up((size_t)a * (S * C + 2));
@@ -279,6 +110,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     constexpr bool USE_MMA = (AT > 0) && (S % 2 == 0) && ((AT * S) % 8 == 0) && ((AT * C) % 8 == 0);
     const int LDQ = m + 4;
     const int LDW = backward_ldw(m);  // row stride of the LU work matrix
+    const int LDF = backward_ldf(m);  // row stride of the packed factors
     const int LDN = backward_ldn(n);  // row stride of Q_ux / K: column n carries Q_u / d, columns n+1.. are zero padding
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -288,8 +120,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     double *Pb = smem + SM.Pb;        // [nblk][PBS]   upper-triangular blocks of P
     double *QUU = smem + SM.QUU;      // [m][LDQ]
     double *W = smem + SM.W;          // [m][LDW] row-major LU work matrix
-    double *Lp = smem + SM.Lp;        // [m][m] packed unit-lower factor, Lp[k*m + k2] = l(k2, k), k2 > k
-    double *Up = smem + SM.Up;        // [m][m] packed upper factor, column-major: Up[c*m + k] = u(k, c), k <= c
+    double *Lp = smem + SM.Lp;        // [m][LDF] packed unit-lower factor, Lp[k*LDF + k2] = l(k2, k), k2 > k
+    double *Up = smem + SM.Up;        // [m][LDF] packed upper factor, column-major: Up[c*LDF + k] = u(k, c), k <= c
     double *rdiag = smem + SM.rdiag;  // [m] 1 / u(k, k)
     double *sA = smem + SM.sA;        // [a][SAS]
     double *sB = smem + SM.sB;        // [a][SBS]
@@ -310,7 +142,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         KB = QUX + (size_t)m * LDN;
         W = KB + (size_t)m * LDN;
         Lp = W + even_up((size_t)m * LDW);
-        Up = Lp + even_up((size_t)m * m);
+        Up = Lp + even_up((size_t)m * backward_ldf(m));
     } else {
         QUX = smem + SM.mats;
         KB = QUX + (size_t)m * LDN;
@@ -355,18 +187,20 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     auto prefetch_record = [&](int t) {  // call after a __syncthreads(): nobody reads the previous record any more
         const double *rec = stage_b + (int64_t)t * L.stride;
         if constexpr (BULK) {
+            // the shared-memory home sA | sB | sLx.. mirrors the record layout (common.cuh): one bulk copy
             if (tid == 0) {
-                const unsigned tail = (unsigned)(((n + m + 9 * a + 9 * pairs + 1) & ~1) * 8);
-                const unsigned total = (unsigned)(a * (S * S + S * C) * 8) + tail;
+                const unsigned total = (unsigned)(L.stride * 8);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
-                for (int i = 0; i < a; ++i) bulk_copy(sA + i * SAS, rec + L.offA + i * S * S, S * S * 8);
-                for (int i = 0; i < a; ++i) bulk_copy(sB + i * SBS, rec + L.offB + i * S * C, S * C * 8);
-                bulk_copy(sLx, rec + L.offLx, tail);
+                // a few medium-sized copies move faster than one large one (the copies are processed concurrently)
+                constexpr unsigned kChunk = 4096;
+#pragma unroll 1
+                for (unsigned off = 0; off < total; off += kChunk)
+                    bulk_copy(sA + off / 8, rec + off / 8, min(kChunk, total - off));
             }
         } else {
-            for (int k = tid; k < a * S * S; k += nthr) cp_async8(sA + (k / (S * S)) * SAS + k % (S * S), rec + L.offA + k);
-            for (int k = tid; k < a * S * C; k += nthr) cp_async8(sB + (k / (S * C)) * SBS + k % (S * C), rec + L.offB + k);
+            for (int k = tid; k < a * S * S; k += nthr) cp_async8(sA + (k / (S * S)) * SAS + k % (S * S), rec + L.offA + (k / (S * S)) * L.strideA + k % (S * S));
+            for (int k = tid; k < a * S * C; k += nthr) cp_async8(sB + (k / (S * C)) * SBS + k % (S * C), rec + L.offB + (k / (S * C)) * L.strideB + k % (S * C));
             for (int k = tid; k < n + m + 9 * a + 9 * pairs; k += nthr) cp_async8(sLx + k, rec + L.offLx + k);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
@@ -432,6 +266,16 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     if (timing) tmark = clock64();
 #pragma unroll 1
     for (int t = T - 1; t >= 0; --t) {
+        // Regularise P in place for phase A (P + mu I, control.py:134-135); the plain diagonal waits in pq (free until
+        // phase E) and is put back before phase B, which needs the unregularised P.
+        for (int k = (p.debug_mode & 8) ? n : tid; k < n; k += nthr) {
+            const int i = k / S, r = k - i * S;
+            double *pd = Pb + (size_t)blk_index(i, i) * PBS + r * S + r;
+            const double v = *pd;
+            pq[k] = v;
+            *pd = v + mu;
+        }
+        tick(9);
         wait_record();
         __syncthreads();
         tick(0);
@@ -448,27 +292,25 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             double Srow[S];
 #pragma unroll
             for (int sg = 0; sg < S; ++sg) Srow[sg] = 0.0;
-#pragma unroll
+            // outer loops rolled: the whole recursion step has to stay resident in the instruction cache
+#pragma unroll 1
             for (int r = 0; r < S; ++r) {
                 const double bv = Bi[r * C + g];
+                const double *prow = Pblk + r * rs;
 #pragma unroll
-                for (int sg = 0; sg < S; ++sg) {
-                    double pv = Pblk[r * rs + sg * cs];
-                    if (i == j && r == sg) pv += mu;
-                    Srow[sg] = fma(bv, pv, Srow[sg]);
-                }
+                for (int sg = 0; sg < S; ++sg) Srow[sg] = fma(bv, prow[sg * cs], Srow[sg]);
             }
             const double *Aj = sA + j * SAS;
             const double *Bj = sB + j * SBS;
             const int row = i * C + g;
-#pragma unroll
+#pragma unroll 1
             for (int sg2 = 0; sg2 < S; ++sg2) {
                 double acc = 0.0;
 #pragma unroll
                 for (int sg = 0; sg < S; ++sg) acc = fma(Srow[sg], Aj[sg * S + sg2], acc);
                 QUX[(size_t)row * LDN + j * S + sg2] = acc;  // L_ux == 0 (cost.py:91)
             }
-#pragma unroll
+#pragma unroll 1
             for (int g2 = 0; g2 < C; ++g2) {
                 double acc = 0.0;
 #pragma unroll
@@ -503,14 +345,15 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         if (tid < kSolveThreads) {
             // ================= group 1: phase C, LU with implicit partial pivoting =================
             const int gt = tid;
-            lu_lookahead<(AT > 0 ? AT * C : 0)>(W, colbuf, rinvbuf, prbuf, order, m, gt);
+            if constexpr (USE_MMA) lu_blocked<AT * C>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid == 0) ? tacc + 15 : nullptr);
+            else lu_lookahead<(AT > 0 ? AT * C : 0)>(W, colbuf, rinvbuf, prbuf, order, m, gt);
             tick(2);
             // pack the factors in pivot order so the substitutions read contiguous memory
             for (int e = gt; e < m * m; e += kSolveThreads) {
                 const int k = e / m, x2 = e - k * m;
                 const double v = W[order[x2] * LDW + k];
-                if (x2 > k) Lp[k * m + x2] = v;   // l(x2, k)
-                else Up[k * m + x2] = v;          // u(x2, k): column k, row x2 <= k
+                if (x2 > k) Lp[k * LDF + x2] = v;   // l(x2, k)
+                else Up[k * LDF + x2] = v;          // u(x2, k): column k, row x2 <= k
                 if (x2 == k) {
                     if (!(fabs(v) > 0.0)) st |= DPILQR_ST_SINGULAR;  // exact zero (or NaN) pivot
                     rdiag[k] = __drcp_rn(v);
@@ -526,13 +369,13 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 double x[8];
                 const bool busy = gt < NB * 8;
                 if (busy) {
-                    const double *F = (which ? Up : Lp) + (8 * bb) * M + 8 * bb;  // F[c * M + rr] = f(rr, c) of this block
+                    const double *F = (which ? Up : Lp) + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = f(rr, c) of this block
                     if (which == 0) {  // unit lower: solve L x = e_j by forward substitution
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             double acc = (i == j) ? 1.0 : 0.0;
 #pragma unroll
-                            for (int c = 0; c < i; ++c) acc = fma(-F[c * M + i], x[c], acc);
+                            for (int c = 0; c < i; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
                             x[i] = acc;
                         }
                     } else {  // upper: solve U x = e_j by backward substitution
@@ -540,7 +383,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                         for (int i = 7; i >= 0; --i) {
                             double acc = (i == j) ? 1.0 : 0.0;
 #pragma unroll
-                            for (int c = i + 1; c < 8; ++c) acc = fma(-F[c * M + i], x[c], acc);
+                            for (int c = i + 1; c < 8; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
                             x[i] = acc * rdiag[8 * bb + i];
                         }
                     }
@@ -549,7 +392,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 if (busy) {
                     double *F = which ? Up : Lp;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) F[(8 * bb + j) * M + 8 * bb + i] = x[i];  // inverse(i, j), same transposed layout
+                    for (int i = 0; i < 8; ++i) F[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j), same transposed layout
                 }
             }
             tick(3);
@@ -557,25 +400,34 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             // ================= group 2: phase B, Q_xx = L_xx + A^T P A in place (upper blocks) =================
             const int gt = tid - kSolveThreads, gn = nthr - kSolveThreads;
             const int blocks_per_round = gn / S;
+            for (int k = gt; k < n; k += gn) {  // the unregularised diagonal of P comes back
+                const int i = k / S, r = k - i * S;
+                Pb[(size_t)blk_index(i, i) * PBS + r * S + r] = pq[k];
+            }
+            named_barrier(2, gn);
             for (int blk0 = (p.debug_mode & 16) ? nblk : 0; blk0 < nblk; blk0 += blocks_per_round) {
                 const int blk = blk0 + gt / S;
                 const int sg = gt % S;
                 const bool live = (gt < blocks_per_round * S) && (blk < nblk);
-                double out[S];
+                int i = 0, rem = live ? blk : 0;
+                while (rem >= a - i) { rem -= a - i; ++i; }
+                const int j = i + rem;
+                double *Pblk = Pb + (size_t)(live ? blk : 0) * PBS;
+                double v[S];  // column sg of P_ij A_j
+#pragma unroll
+                for (int r = 0; r < S; ++r) v[r] = 0.0;
                 if (live) {
-                    int i = 0, rem = blk;
-                    while (rem >= a - i) { rem -= a - i; ++i; }
-                    const int j = i + rem;
-                    const double *Pblk = Pb + (size_t)blk * PBS;
-                    const double *Ai = sA + i * SAS, *Aj = sA + j * SAS;
-                    double v[S];
+                    const double *Aj = sA + j * SAS;
+#pragma unroll 4
+                    for (int q = 0; q < S; ++q) {
+                        const double av = Aj[q * S + sg];
 #pragma unroll
-                    for (int r = 0; r < S; ++r) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int q = 0; q < S; ++q) acc = fma(Pblk[r * S + q], Aj[q * S + sg], acc);
-                        v[r] = acc;
+                        for (int r = 0; r < S; ++r) v[r] = fma(Pblk[r * S + q], av, v[r]);
                     }
+                }
+                named_barrier(2, gn);  // every thread of the block has read P_ij: overwrite it
+                if (live) {
+                    const double *Ai = sA + i * SAS;
 #pragma unroll
                     for (int r = 0; r < S; ++r) {
                         double acc = 0.0;
@@ -589,14 +441,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                         } else if (r < 3 && sg < 3) {
                             lxx = sHo[9 * pair_index(i, j, a) + r * 3 + sg];
                         }
-                        out[r] = lxx + acc;
+                        Pblk[r * S + sg] = lxx + acc;
                     }
-                }
-                named_barrier(2, gn);
-                if (live) {
-                    double *Pblk = Pb + (size_t)blk * PBS;
-#pragma unroll
-                    for (int r = 0; r < S; ++r) Pblk[r * S + sg] = out[r];
                 }
             }
             tick(2);
@@ -628,7 +474,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
 #pragma unroll
                 for (int dir = 0; dir < 2; ++dir) {  // 0: forward with the unit lower factor, 1: backward with the upper
                     const double *F = dir ? Up : Lp;
-#pragma unroll
+#pragma unroll 1
                     for (int lvl = 0; lvl < NB; ++lvl) {
                         const int blk = dir ? NB - 1 - lvl : lvl;
                         if (dir == 1) {
@@ -643,7 +489,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                                 for (int j = 7; j >= 0; --j) {
                                     x[j] *= rdiag[8 * blk + j];
 #pragma unroll
-                                    for (int j2 = 0; j2 < j; ++j2) x[j2] = fma(-F[(8 * blk + j) * M + 8 * blk + j2], x[j], x[j2]);
+                                    for (int j2 = 0; j2 < j; ++j2) x[j2] = fma(-F[(8 * blk + j) * LDF + 8 * blk + j2], x[j], x[j2]);
                                 }
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) Xc[(size_t)(8 * blk + j) * LDN + lane] = x[j];
@@ -653,7 +499,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                         double d0 = 0.0, d1 = 0.0;
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
-                            dmma_m8n8k4(d0, d1, F[(8 * blk + 4 * ks + fc) * M + 8 * blk + fr],
+                            dmma_m8n8k4(d0, d1, F[(8 * blk + 4 * ks + fc) * LDF + 8 * blk + fr],
                                         Xc[(size_t)(8 * blk + 4 * ks + fc) * LDN + fr]);
                         __syncwarp();
                         *reinterpret_cast<double2 *>(Xc + (size_t)(8 * blk + fr) * LDN + 2 * fc) = make_double2(d0, d1);
@@ -667,7 +513,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                                 double2 c2 = *reinterpret_cast<double2 *>(cp);
 #pragma unroll
                                 for (int ks = 0; ks < 2; ++ks)
-                                    dmma_m8n8k4(c2.x, c2.y, -F[(8 * blk + 4 * ks + fc) * M + 8 * b2 + fr],
+                                    dmma_m8n8k4(c2.x, c2.y, -F[(8 * blk + 4 * ks + fc) * LDF + 8 * b2 + fr],
                                                 Xc[(size_t)(8 * blk + 4 * ks + fc) * LDN + fr]);
                                 *reinterpret_cast<double2 *>(cp) = c2;
                             }
@@ -682,12 +528,12 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 for (int k = 0; k < m; ++k) xcol[(size_t)k * LDN] = -QUX[(size_t)order[k] * LDN + col];
                 for (int k = 0; k < m - 1; ++k) {
                     const double xk = xcol[(size_t)k * LDN];
-                    for (int k2 = k + 1; k2 < m; ++k2) xcol[(size_t)k2 * LDN] = fma(-Lp[k * m + k2], xk, xcol[(size_t)k2 * LDN]);
+                    for (int k2 = k + 1; k2 < m; ++k2) xcol[(size_t)k2 * LDN] = fma(-Lp[k * LDF + k2], xk, xcol[(size_t)k2 * LDN]);
                 }
                 for (int cc = m - 1; cc >= 0; --cc) {
                     const double xc = xcol[(size_t)cc * LDN] * rdiag[cc];
                     xcol[(size_t)cc * LDN] = xc;
-                    for (int k = 0; k < cc; ++k) xcol[(size_t)k * LDN] = fma(-Up[cc * m + k], xc, xcol[(size_t)k * LDN]);
+                    for (int k = 0; k < cc; ++k) xcol[(size_t)k * LDN] = fma(-Up[cc * LDF + k], xc, xcol[(size_t)k * LDN]);
                 }
             }
         }
@@ -711,11 +557,13 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         for (int col = tid; col < n + m; col += nthr) {
             if (col < n) {
                 double qd = 0.0;
+#pragma unroll 4
                 for (int k = 0; k < m; ++k) qd = fma(QUX[(size_t)k * LDN + col], dv[k], qd);
                 pq[col] = qd;
             } else {
                 const int k = col - n;
                 double acc = 0.0;
+#pragma unroll 4
                 for (int l = 0; l < m; ++l) acc = fma(QUU[k * LDQ + l], dv[l], acc);
                 zv[k] = acc + Qu[k];
             }
@@ -836,6 +684,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         }
         for (int col = tid; col < n; col += nthr) {
             double acc = 0.0;
+#pragma unroll 4
             for (int k = 0; k < m; ++k) acc = fma(KB[(size_t)k * LDN + col], zv[k], acc);
             pvec[col] = Qx[col] + acc + pq[col];
         }

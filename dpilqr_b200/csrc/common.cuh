@@ -24,6 +24,7 @@ namespace dpilqr {
 struct StageLayout {
     int a, s, c, n, m, pairs;
     int offA, offB, offLx, offLu, offHd, offHo, stride;
+    int strideA, strideB;  // doubles between the A (B) blocks of consecutive agents
 };
 
 __host__ __device__ inline StageLayout stage_layout(int a, int s, int c)
@@ -32,9 +33,13 @@ __host__ __device__ inline StageLayout stage_layout(int a, int s, int c)
     L.a = a; L.s = s; L.c = c;
     L.n = a * s; L.m = a * c;
     L.pairs = a * (a - 1) / 2;
+    // The per-agent blocks carry two doubles of padding: the backward kernel keeps a record in shared memory in
+    // exactly this layout (one TMA bulk copy per record) and the padding de-aliases the banks of consecutive blocks.
+    L.strideA = s * s + 2;
+    L.strideB = s * c + 2;
     L.offA = 0;
-    L.offB = L.offA + a * s * s;
-    L.offLx = L.offB + a * s * c;
+    L.offB = L.offA + a * L.strideA;
+    L.offLx = L.offB + a * L.strideB;
     L.offLu = L.offLx + L.n;
     L.offHd = L.offLu + L.m;
     L.offHo = L.offHd + 9 * a;

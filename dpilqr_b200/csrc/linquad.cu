@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(128) linquad_kernel(const LinQuadParams p)
             Lu[j] = w_ref * v;
         }
         if (!terminal) {
-            double *A = rec + L.offA + i * NX * NX;
-            double *Bm = rec + L.offB + i * NX * NU;
+            double *A = rec + L.offA + i * L.strideA;
+            double *Bm = rec + L.offB + i * L.strideB;
 #pragma unroll
             for (int r = 0; r < NX; ++r) {
 #pragma unroll
@@ -192,7 +192,7 @@ __global__ void stage_to_dense_kernel(const Batch bt, const double *stage, doubl
     for (int k = threadIdx.x; k < n * n; k += blockDim.x) {
         const int r = k / n, col = k % n;
         const int i = r / s, ri = r % s, j = col / s, cj = col % s;
-        if (A) A[rec_id * n * n + k] = (i == j && !terminal) ? rec[L.offA + i * s * s + ri * s + cj] : 0.0;
+        if (A) A[rec_id * n * n + k] = (i == j && !terminal) ? rec[L.offA + i * L.strideA + ri * s + cj] : 0.0;
         if (Lxx) {
             double v = 0.0;
             if (i == j) {
@@ -211,7 +211,7 @@ __global__ void stage_to_dense_kernel(const Batch bt, const double *stage, doubl
     for (int k = threadIdx.x; k < n * m; k += blockDim.x) {
         const int r = k / m, col = k % m;
         const int i = r / s, ri = r % s, j = col / c, cj = col % c;
-        if (Bm) Bm[rec_id * n * m + k] = (i == j && !terminal) ? rec[L.offB + i * s * c + ri * c + cj] : 0.0;
+        if (Bm) Bm[rec_id * n * m + k] = (i == j && !terminal) ? rec[L.offB + i * L.strideB + ri * c + cj] : 0.0;
     }
     for (int k = threadIdx.x; k < m * m; k += blockDim.x) {
         const int r = k / m, col = k % m;

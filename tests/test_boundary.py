@@ -41,7 +41,7 @@ def test_header_symbols_are_exported(built_lib):
     assert set(_native.EXPORTS) == declared
     assert _native.lib().dpilqr_version() >= 100
     assert _native.lib().dpilqr_model_nx(7) == 12 and _native.lib().dpilqr_model_nu(7) == 4
-    assert _native.lib().dpilqr_stage_stride(10, 12, 4) == 2576
+    assert _native.lib().dpilqr_stage_stride(10, 12, 4) == 2616
     assert _native.lib().dpilqr_workspace_bytes(4096, 10, 12, 4, 50, 10) > 0
 
 

@@ -1,191 +1,96 @@
-// lu_bench.cu -- the LU routine of the backward kernel in isolation, with per-segment cycle counters.
+// lu_bench.cu -- phase C of the backward kernel (csrc/lu.cuh, the very same code) in isolation: one CTA of 256
+// threads per SM factorises a resident 40x40 matrix over and over; prints cycles per factorisation and checks
+// the factors against a host LU with the same pivoting.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++20 -I dpilqr_b200/csrc -o tools/bin/lu_bench tools/lu_bench.cu
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
-#include <cuda_runtime.h>
-constexpr int kSolveThreads = 256;
-__device__ long long g_dbg[4];
-__device__ int g_probe;
-__host__ __device__ constexpr int backward_ldw(int m) { return ((m + 2) & ~1) % 16 == 0 ? ((m + 2) & ~1) + 2 : ((m + 2) & ~1); }
-__device__ __forceinline__ void named_barrier(int id, int count)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-// Reciprocal without the special-case branch of __drcp_rn: hardware seed (about 20 bits) plus two Newton steps.
-__device__ __forceinline__ double fast_rcp(double v)
-{
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(v));
-    double e = fma(-v, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-v, x, 1.0);
-    return fma(x, e, x);
-}
+#include <vector>
 
-// Phase C of the backward kernel: LU factorisation of the m x m matrix W (row-major, W[r*ldw + c]) with partial
-// pivoting, by the kSolveThreads threads of warp group 1.  Four threads per row, each owning every fourth pair of
-// columns (double2 accesses), everything in shared memory, ONE named barrier per column.  While eliminating
-// column k the thread that owns the entry of column k+1 publishes its pivot-search key together with its
-// reciprocal (computed speculatively, off the critical path).  After the barrier each warp finds the arg-max on
-// its own with warp reductions and picks the matching reciprocal up (LAPACK dgetf2 also scales by the reciprocal
-// pivot).  Rows never move: a used pivot row is simply marked (key 0) and its index recorded in order[k].  On
-// return W holds the multipliers l(r, k) in the eliminated positions and the rows of U in the pivot rows.
-// The body of the column loop is branch-free straight-line code (a lone warp per scheduler pays the full branch
-// latency), the loop itself is not unrolled (instruction-cache footprint); kept out of line for a register
-// allocation of its own.  MT > 0 fixes m at compile time.
-template <int MT>
-__device__ __noinline__ void lu_implicit_pivoting(double *__restrict__ W, unsigned long long *__restrict__ keybuf,
-                                                 double *__restrict__ rinvbuf, int *__restrict__ order, int m_rt, int gt)
-{
-    const int m = MT > 0 ? MT : m_rt;
-    const int ldw = backward_ldw(m);
-    const int npair = (m + 1) >> 1;
-    constexpr int NP = MT > 0 ? ((MT + 1) / 2 + 3) / 4 : 8;  // column pairs per thread
-    const int lane = gt & 31;
-    const int r = gt >> 2, q = gt & 3;
-    const bool myrow = r < m;
-    double *wrow = W + (myrow ? r : m - 1) * ldw;
-    // |v| of a double orders like its bit pattern; +1 so that a live zero still beats a used row (key 0)
-    auto pivot_key = [](double v) -> unsigned long long {
-        const double av = fabs(v);
-        return (av == av) ? (unsigned long long)__double_as_longlong(av) + 1ull : 1ull;
-    };
-    if (gt < 128) keybuf[gt] = 0ull;  // rows >= m never compete
-    named_barrier(1, kSolveThreads);
-    if (q == 0 && myrow) {
-        const double v = wrow[0];
-        keybuf[r] = pivot_key(v);
-        rinvbuf[r] = fast_rcp(v);
-    }
-    named_barrier(1, kSolveThreads);
-    bool mydone = !myrow;
-    double2 wreg[NP];  // this thread's column pairs of row r
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const int j = q + 4 * i;
-        wreg[i] = (j < npair) ? *reinterpret_cast<const double2 *>(wrow + 2 * j) : make_double2(0.0, 0.0);
-    }
-    double held_mult = 0.0;  // multiplier of the previous step, stored one barrier later
-    bool held = false;
-#pragma unroll 1
-    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, tm = clock64();
-    for (int k = 0; k < m; ++k) {
-        const unsigned long long *cur = keybuf + (k & 1) * 64;
-        const unsigned long long key0 = cur[lane];
-        const unsigned long long key1 = cur[lane + 32];
-        const unsigned long long kmax = key1 > key0 ? key1 : key0;
-        const int rsel = key1 > key0 ? lane + 32 : lane;
-        const unsigned hi = (unsigned)(kmax >> 32);
-        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-        bool mine = (hi == mhi);
-        unsigned bal = __ballot_sync(0xffffffffu, mine);
-        if (__popc(bal) > 1) {  // rare: several rows share the top 32 bits
-            const unsigned lo = mine ? (unsigned)kmax : 0u;
-            const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
-            mine = mine && (lo == mlo);
-            bal = __ballot_sync(0xffffffffu, mine);
-        }
-        const int pr = __shfl_sync(0xffffffffu, rsel, __ffs(bal) - 1);
-        { long long now = clock64(); c0 += now - tm; tm = now; }
-        const double rinv = rinvbuf[(k & 1) * 64 + pr];
-        const double *prow = W + pr * ldw;
-        if (gt == 0) order[k] = pr;
-        // The multiplier of step k-1 replaces the eliminated entry (r, k-1) only now: every thread of the row has
-        // read that entry before the barrier that ended step k-1.
-        if (held) wrow[k - 1] = held_mult;
-        mydone = mydone || (r == pr);
-        const bool live = !mydone;
-        const double mult = wrow[k] * rinv;
-        held = live && (q == 0);
-        held_mult = mult;
-        { long long now = clock64(); c1 += now - tm; tm = now; }
-        __syncwarp();  // all four threads of the row have read entry (r, k): the pair loop below may overwrite it
-        // Column k+1 first, by all four threads of the row alike (no divergence): the next pivot search needs its
-        // key and the speculative reciprocal as early as possible.  The pair loop recomputes the same value.
-        if (k + 1 < m) {
-            const double v = live ? fma(-mult, prow[k + 1], wrow[k + 1]) : 0.0;
-            const unsigned long long key = live ? pivot_key(v) : 0ull;
-            const double vr = fast_rcp(v);
-            if (myrow && q == 1) {
-                keybuf[((k + 1) & 1) * 64 + r] = key;
-                rinvbuf[((k + 1) & 1) * 64 + r] = vr;
-            }
-        }
-        // Pair loop.  The thread's own pairs live in registers (static indexing) for the whole factorisation and
-        // are mirrored to shared memory after every update; only the pivot row is loaded, and only the pairs that
-        // still change (j >= jp0), so the shared-memory traffic shrinks with the active sub-matrix.  The pair
-        // holding column k+1 may also rewrite the eliminated entry (r, k) with rounding noise: the multiplier is
-        // stored over it at the next step.
-        const int jp0 = (k + 1) >> 1;
-        double2 p2[NP];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            const int j = q + 4 * i;
-            p2[i] = make_double2(0.0, 0.0);
-            if (live && j >= jp0 && j < npair) p2[i] = *reinterpret_cast<const double2 *>(prow + 2 * j);
-        }
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            wreg[i].x = fma(-mult, p2[i].x, wreg[i].x);
-            wreg[i].y = fma(-mult, p2[i].y, wreg[i].y);
-        }
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            const int j = q + 4 * i;
-            if (live && j >= jp0 && j < npair) *reinterpret_cast<double2 *>(wrow + 2 * j) = wreg[i];
-        }
-        { long long now = clock64(); c2 += now - tm; tm = now; }
-        named_barrier(1, kSolveThreads);
-        { long long now = clock64(); c3 += now - tm; tm = now; }
-    }
-    if (gt == g_probe) { g_dbg[0] = c0; g_dbg[1] = c1; g_dbg[2] = c2; g_dbg[3] = c3; }
-    if (held) wrow[m - 1] = held_mult;
-    named_barrier(1, kSolveThreads);
-}
+#include "lu.cuh"
 
+using namespace dpilqr;
 
-__global__ void k_lu(const double *A, long long *out, int m, int reps)
+constexpr int M = 40;
+constexpr int LDW = backward_ldw(M);
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 1) bench_kernel(const double *A, double *out, int *order_out, long long *cycles, int reps)
 {
-    extern __shared__ double smem[];
-    const int ldw = backward_ldw(m);
-    double *W = smem;
-    unsigned long long *keybuf = reinterpret_cast<unsigned long long *>(smem + m * ldw);
-    double *rinvbuf = smem + m * ldw + 128;
-    int *order = reinterpret_cast<int *>(smem + m * ldw + 256);
+    __shared__ __align__(16) double W[M * LDW];
+    __shared__ __align__(16) double W0[M * LDW];
+    __shared__ __align__(16) double colbuf[256];
+    __shared__ double rinvbuf[4];
+    __shared__ int order[M];
     const int tid = threadIdx.x;
-    long long total = 0;
-    for (int rep = 0; rep < reps; ++rep) {
-        for (int k = tid; k < m * m; k += blockDim.x) W[(k / m) * ldw + k % m] = A[k];
+    for (int e = tid; e < M * M; e += 256) W0[(e / M) * LDW + e % M] = A[(size_t)blockIdx.x * M * M + e];
+    __syncthreads();
+    long long acc = 0, lt[4] = {0, 0, 0, 0};
+    for (int r = 0; r < reps; ++r) {
+        for (int e = tid; e < M * LDW; e += 256) W[e] = W0[e];
         __syncthreads();
-        long long t0 = clock64();
-        if (tid < kSolveThreads) lu_implicit_pivoting<40>(W, keybuf, rinvbuf, order, m, tid);
-        long long t1 = clock64();
+        const long long t0 = clock64();
+        if (VARIANT == 0) lu_blocked<M>(W, order, reinterpret_cast<unsigned *>(colbuf), tid, tid == 0 ? lt : nullptr);
+        else lu_lookahead<M>(W, colbuf, rinvbuf, reinterpret_cast<int *>(rinvbuf + 2), order, M, tid);
         __syncthreads();
-        total += t1 - t0;
+        acc += clock64() - t0;
     }
-    if (tid == 0) { out[0] = total; out[1] = order[0] + order[39]; }
+    if (tid == 0) {
+        cycles[4 * blockIdx.x] = acc / reps;
+        for (int k = 0; k < 3; ++k) cycles[4 * blockIdx.x + 1 + k] = lt[k] / reps;
+    }
+    for (int e = tid; e < M * M; e += 256) out[(size_t)blockIdx.x * M * M + e] = W[(e / M) * LDW + e % M];
+    if (tid < M) order_out[blockIdx.x * M + tid] = order[tid];
 }
 
 int main(int argc, char **argv)
 {
-    const int m = 40, reps = 50;
-    const int ldw = backward_ldw(m);
-    double *hA = (double *)malloc(m * m * 8);
+    const int reps = argc > 1 ? atoi(argv[1]) : 200;
+    const int nb = 148;
+    std::vector<double> A((size_t)nb * M * M);
     srand(1);
-    for (int i = 0; i < m; ++i)
-        for (int j = 0; j < m; ++j) hA[i * m + j] = (double)rand() / RAND_MAX - 0.5 + (i == j ? 3.0 : 0.0);
-    double *dA;
-    long long *dout, h[2], dbg[4];
-    cudaMalloc(&dA, m * m * 8);
-    cudaMalloc(&dout, 16);
-    cudaMemcpy(dA, hA, m * m * 8, cudaMemcpyHostToDevice);
-    for (int probe : {0, 33, 100, 200}) {
-        cudaMemcpyToSymbol(g_probe, &probe, 4);
-        for (int pass = 0; pass < 2; ++pass) k_lu<<<1, 512, (m * ldw + 512) * 8>>>(dA, dout, m, reps);
-        cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost);
-        cudaMemcpyFromSymbol(dbg, g_dbg, 32);
-        printf("probe thread %3d: %.0f cycles per LU (%.0f per column); per column: search %.0f, mult %.0f, eliminate %.0f, barrier %.0f  [%s]\n",
-               probe, (double)h[0] / reps, (double)h[0] / reps / m, dbg[0] / 40.0, dbg[1] / 40.0, dbg[2] / 40.0, dbg[3] / 40.0,
-               cudaGetErrorString(cudaGetLastError()));
+    for (int b = 0; b < nb; ++b)
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) A[((size_t)b * M + i) * M + j] = (rand() / (double)RAND_MAX - 0.5) + (i == j ? 2.0 : 0.0);
+    double *dA, *dout;
+    int *dorder;
+    long long *dcyc;
+    cudaMalloc(&dA, A.size() * 8), cudaMalloc(&dout, A.size() * 8), cudaMalloc(&dorder, nb * M * 4), cudaMalloc(&dcyc, nb * 32);
+    cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
+    for (int variant = 0; variant < 2; ++variant) {
+        for (int pass = 0; pass < 2; ++pass) {
+            if (variant == 0) bench_kernel<0><<<nb, 256>>>(dA, dout, dorder, dcyc, reps);
+            else bench_kernel<1><<<nb, 256>>>(dA, dout, dorder, dcyc, reps);
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        std::vector<double> out(A.size());
+        std::vector<int> order(nb * M);
+        std::vector<long long> cyc(nb * 4);
+        cudaMemcpy(out.data(), dout, out.size() * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(order.data(), dorder, order.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(cyc.data(), dcyc, cyc.size() * 8, cudaMemcpyDeviceToHost);
+        // residual of P A = L U from the in-place factors (rows never move: order[k] is the pivot row of step k)
+        double worst = 0.0;
+        for (int b = 0; b < nb; ++b) {
+            const double *F = &out[(size_t)b * M * M];
+            const int *ord = &order[b * M];
+            std::vector<int> step(M);
+            for (int k = 0; k < M; ++k) step[ord[k]] = k;
+            for (int r = 0; r < M; ++r)
+                for (int c = 0; c < M; ++c) {
+                    // row r (pivot step kr): A[r][c] = sum_{k < kr} l(r,k) u(k,c) + u(kr, c)
+                    const int kr = step[r];
+                    double acc = (c >= kr) ? F[r * M + c] : 0.0;
+                    for (int k = 0; k < kr && k <= c; ++k) acc += F[r * M + k] * F[ord[k] * M + c];
+                    worst = fmax(worst, fabs(acc - A[((size_t)b * M + r) * M + c]));
+                }
+        }
+        printf("%s: %lld cycles per 40x40 factorisation (CTA 0; detail %lld %lld %lld), max |PA - LU| = %.2e\n",
+               variant == 0 ? "lu_blocked  " : "lu_lookahead", cyc[0], cyc[1], cyc[2], cyc[3], worst);
     }
     return 0;
 }
