@@ -33,7 +33,7 @@ struct TileSize {
 };
 
 struct BackwardSmem {
-    size_t Pb, QUU, W, Lp, Up, rdiag, sA, sB, sL, pvec, Qx, pq, Qu, dv, zv, order, keys, rinv, tacc, mbar, mats, total_doubles;
+    size_t Pb, QUU, W, Lp, Up, rdiag, sA, sB, sL, pvec, Qx, pq, Qu, dv, zv, order, keys, rinv, scal, tacc, mbar, mats, total_doubles;
 };
 
 // Row stride of the Q_ux / K buffers: room for right-hand side n (Q_u) rounded up to a tile of 8, and congruent to
@@ -85,7 +85,8 @@ __host__ __device__ constexpr BackwardSmem backward_smem(int a, int S, int C, bo
     L.order = off; off += even_up(((size_t)m + 1) / 2 + 1);  // m ints
     L.keys = off;  off += 256;                                 // look-ahead side buffer of the LU
     L.rinv = off;  off += 4;                                   // reciprocal pivots + pivot rows of two rounds
-    L.tacc = off;  off += 20;                                  // debug cycle counters
+    L.scal = off;  off += 2;                                   // mu, reference-cost weight
+    L.tacc = off;  off += 28;                                  // debug cycle counters
     L.mbar = off;  off += 2;                                   // mbarrier of the stage-record bulk copies
     L.mats = off;
     if (mats_in_smem) off += 2 * (size_t)m * backward_ldn(n);
@@ -93,7 +94,7 @@ __host__ __device__ constexpr BackwardSmem backward_smem(int a, int S, int C, bo
     return L;
 }
 
-template <int S, int C, int AT, bool GLOBAL>
+template <int S, int C, int AT, bool GLOBAL, bool TIMED>
 __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p)
 {
     extern __shared__ double smem[];
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     const int LDW = backward_ldw(m);  // row stride of the LU work matrix
     const int LDF = backward_ldf(m);  // row stride of the packed factors
     const int LDN = backward_ldn(n);  // row stride of Q_ux / K: column n carries Q_u / d, columns n+1.. are zero padding
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    constexpr int nthr = 512;  // launch_backward always starts 512 threads
+    const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const StageLayout L = stage_layout(a, S, C);
     const BackwardSmem SM = backward_smem(a, S, C, !GLOBAL);
@@ -148,24 +150,35 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         KB = QUX + (size_t)m * LDN;
     }
 
-    const int32_t *cidx_b = bt.cost_idx + (int64_t)b * a;
-    const double w_ref = bt.weights ? bt.weights[2 * b] : 1.0;
-    const double mu = p.mu[b];
-    const double *stage_b = p.stage + (int64_t)b * (T + 1) * L.stride;
-    double *Kb = p.K + (int64_t)b * T * m * n;
-    double *db = p.d + (int64_t)b * T * m;
+    // The kernel is capped at 128 registers and local memory has next to no L1 behind it (227 kB of shared memory
+    // carved out): per-problem pointers are re-derived from b where they are used (the opaque copy keeps the compiler
+    // from hoisting them into registers that live for the whole recursion) and the two per-problem scalars sit in
+    // shared memory.
+    auto problem = [b]() {
+        int v = b;
+        asm volatile("" : "+r"(v));
+        return v;
+    };
+    auto cost_row = [&](int i) { return (int64_t)bt.cost_idx[(int64_t)problem() * a + i]; };
+    double *scal = smem + SM.scal;  // [0] mu, [1] weight of the reference cost
+    if (threadIdx.x == 0) {
+        scal[0] = p.mu[b];
+        scal[1] = bt.weights ? bt.weights[2 * b] : 1.0;
+    }
     int st = 0;
     // optional per-phase cycle counters (debug aid, see dpilqr_debug_backward_timing); kept in shared memory
-    long long *tacc = reinterpret_cast<long long *>(smem + SM.tacc) + (tid == 0 ? 0 : 12);
+    long long *tacc = reinterpret_cast<long long *>(smem + SM.tacc) + (tid < 32 ? 0 : 12);
     long long tmark = 0;
-    const bool timing = (p.timing != nullptr) && (blockIdx.x == 0) && (tid == 0 || tid == kSolveThreads);
-    if (timing) {
-        for (int k = 0; k < (tid == 0 ? 12 : 8); ++k) tacc[k] = 0;
+    constexpr int kTimedThread2 = 160;  // first thread of warp group 2 (warp 1) in the instrumented tensor-path build
+    const bool timing = TIMED && (p.timing != nullptr) && (blockIdx.x == 0) && ((tid >> 5) == 0 || (tid >> 5) == (kTimedThread2 >> 5));  // whole warps: no divergence from timing
+    if (timing && (tid & 31) == 0) {
+        for (int k = 0; k < 12; ++k) tacc[k] = 0;
+        if (tid == 0) tacc[24] = tacc[25] = tacc[26] = 0;
     }
     auto tick = [&](int slot) {
         if (timing) {
             const long long now = clock64();
-            tacc[slot] += now - tmark;
+            if ((tid & 31) == 0) tacc[slot] += now - tmark;
             tmark = now;
         }
     };
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                      ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
     };
     auto prefetch_record = [&](int t) {  // call after a __syncthreads(): nobody reads the previous record any more
-        const double *rec = stage_b + (int64_t)t * L.stride;
+        const double *rec = p.stage + ((int64_t)problem() * (T + 1) + t) * L.stride;
         if constexpr (BULK) {
             // the shared-memory home sA | sB | sLx.. mirrors the record layout (common.cuh): one bulk copy
             if (tid == 0) {
@@ -251,8 +264,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         const int j = i + rem;
         double v = 0.0;
         if (i == j) {
-            const double *Qf = bt.Qf + (int64_t)cidx_b[i] * S * S;
-            v = w_ref * (Qf[r * S + cc] + Qf[cc * S + r]);
+            const double *Qf = bt.Qf + cost_row(i) * S * S;
+            v = scal[1] * (Qf[r * S + cc] + Qf[cc * S + r]);
             if (r < 3 && cc < 3) v += sHd[9 * i + r * 3 + cc];
         } else if (r < 3 && cc < 3) {
             v = sHo[9 * pair_index(i, j, a) + r * 3 + cc];
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             double *pd = Pb + (size_t)blk_index(i, i) * PBS + r * S + r;
             const double v = *pd;
             pq[k] = v;
-            *pd = v + mu;
+            *pd = v + scal[0];
         }
         tick(9);
         wait_record();
@@ -316,8 +329,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
 #pragma unroll
                 for (int sg = 0; sg < S; ++sg) acc = fma(Srow[sg], Bj[sg * C + g2], acc);
                 if (i == j) {
-                    const double *R = bt.R + (int64_t)cidx_b[i] * C * C;
-                    acc += w_ref * (R[g * C + g2] + R[g2 * C + g]);
+                    const double *R = bt.R + cost_row(i) * C * C;
+                    acc += scal[1] * (R[g * C + g2] + R[g2 * C + g]);
                 }
                 QUU[row * LDQ + j * C + g2] = acc;
                 W[row * LDW + j * C + g2] = acc;
@@ -342,63 +355,23 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         __syncthreads();
         tick(1);
 
-        if (tid < kSolveThreads) {
+        // Two warp groups run side by side.  Tensor-path kernels split by scheduler: the warps of SM sub-partition 0
+        // (warp % 4 == 0) factorise Q_uu -- the panel warp is latency-bound and keeps its FP64 pipe to itself -- while
+        // the twelve warps of the other sub-partitions compute Q_xx.  Otherwise: first 256 threads / the rest.
+        constexpr int kLuThreads = USE_MMA ? 128 : kSolveThreads;
+        const bool lu_group = tid < kLuThreads;
+        const bool idle_group = USE_MMA && !lu_group && ((warp & 3) == 0);  // shares the scheduler of the panel warp
+        if (lu_group) {
             // ================= group 1: phase C, LU with implicit partial pivoting =================
             const int gt = tid;
-            if constexpr (USE_MMA) lu_blocked<AT * C>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid == 0) ? tacc + 15 : nullptr);
+            if constexpr (USE_MMA)
+                lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid < 32) ? tacc + 24 : nullptr);
             else lu_lookahead<(AT > 0 ? AT * C : 0)>(W, colbuf, rinvbuf, prbuf, order, m, gt);
             tick(2);
-            // pack the factors in pivot order so the substitutions read contiguous memory
-            for (int e = gt; e < m * m; e += kSolveThreads) {
-                const int k = e / m, x2 = e - k * m;
-                const double v = W[order[x2] * LDW + k];
-                if (x2 > k) Lp[k * LDF + x2] = v;   // l(x2, k)
-                else Up[k * LDF + x2] = v;          // u(x2, k): column k, row x2 <= k
-                if (x2 == k) {
-                    if (!(fabs(v) > 0.0)) st |= DPILQR_ST_SINGULAR;  // exact zero (or NaN) pivot
-                    rdiag[k] = __drcp_rn(v);
-                }
-            }
-            if constexpr (USE_MMA) {
-                // The blocked forward solve of phase D applies the 8x8 diagonal blocks of the unit lower factor (well
-                // conditioned: |l| <= 1) as explicit inverses on the tensor path: invert them here, in place.  One
-                // thread per (block, column of the inverse).
-                constexpr int M = AT * C, NB = M / 8;
-                named_barrier(1, kSolveThreads);
-                const int which = gt / (NB * 8), bb = (gt / 8) % NB, j = gt & 7;  // which: 0 = L, 1 = U
-                double x[8];
-                const bool busy = gt < NB * 8;
-                if (busy) {
-                    const double *F = (which ? Up : Lp) + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = f(rr, c) of this block
-                    if (which == 0) {  // unit lower: solve L x = e_j by forward substitution
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            double acc = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-                            for (int c = 0; c < i; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
-                            x[i] = acc;
-                        }
-                    } else {  // upper: solve U x = e_j by backward substitution
-#pragma unroll
-                        for (int i = 7; i >= 0; --i) {
-                            double acc = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-                            for (int c = i + 1; c < 8; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
-                            x[i] = acc * rdiag[8 * bb + i];
-                        }
-                    }
-                }
-                named_barrier(1, kSolveThreads);
-                if (busy) {
-                    double *F = which ? Up : Lp;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) F[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j), same transposed layout
-                }
-            }
-            tick(3);
-        } else {
+        } else if (!idle_group) {
             // ================= group 2: phase B, Q_xx = L_xx + A^T P A in place (upper blocks) =================
-            const int gt = tid - kSolveThreads, gn = nthr - kSolveThreads;
+            const int gt = USE_MMA ? ((((warp >> 2) - 1) * 3 + (warp & 3) - 1) << 5) + lane : tid - kSolveThreads;
+            const int gn = USE_MMA ? 288 : nthr - kLuThreads;
             const int blocks_per_round = gn / S;
             for (int k = gt; k < n; k += gn) {  // the unregularised diagonal of P comes back
                 const int i = k / S, r = k - i * S;
@@ -414,38 +387,102 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 const int j = i + rem;
                 double *Pblk = Pb + (size_t)(live ? blk : 0) * PBS;
                 double v[S];  // column sg of P_ij A_j
-#pragma unroll
-                for (int r = 0; r < S; ++r) v[r] = 0.0;
                 if (live) {
                     const double *Aj = sA + j * SAS;
-#pragma unroll 4
-                    for (int q = 0; q < S; ++q) {
-                        const double av = Aj[q * S + sg];
+                    double acol[S];
 #pragma unroll
-                        for (int r = 0; r < S; ++r) v[r] = fma(Pblk[r * S + q], av, v[r]);
+                    for (int q = 0; q < S; ++q) acol[q] = Aj[q * S + sg];
+#pragma unroll
+                    for (int r = 0; r < S; ++r) {
+                        double acc = 0.0;
+                        if constexpr (S % 2 == 0) {  // two entries of P_ij per 16-byte load: half the shared-memory requests
+#pragma unroll
+                            for (int q = 0; q < S; q += 2) {
+                                const double2 pp = *reinterpret_cast<const double2 *>(Pblk + r * S + q);
+                                acc = fma(pp.y, acol[q + 1], fma(pp.x, acol[q], acc));
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < S; ++q) acc = fma(Pblk[r * S + q], acol[q], acc);
+                        }
+                        v[r] = acc;
                     }
                 }
                 named_barrier(2, gn);  // every thread of the block has read P_ij: overwrite it
                 if (live) {
                     const double *Ai = sA + i * SAS;
+                    const double w_ref = scal[1];
+                    constexpr int RS = (S % 2 == 0) ? 2 : 1;  // rows of A_i^T per 16-byte load
 #pragma unroll
-                    for (int r = 0; r < S; ++r) {
-                        double acc = 0.0;
+                    for (int r = 0; r < S; r += RS) {
+                        double acc[RS];
 #pragma unroll
-                        for (int q = 0; q < S; ++q) acc = fma(Ai[q * S + r], v[q], acc);
-                        double lxx = 0.0;
-                        if (i == j) {
-                            const double *Q = bt.Q + (int64_t)cidx_b[i] * S * S;
-                            lxx = w_ref * (Q[r * S + sg] + Q[sg * S + r]);
-                            if (r < 3 && sg < 3) lxx += sHd[9 * i + r * 3 + sg];
-                        } else if (r < 3 && sg < 3) {
-                            lxx = sHo[9 * pair_index(i, j, a) + r * 3 + sg];
+                        for (int e = 0; e < RS; ++e) acc[e] = 0.0;
+#pragma unroll
+                        for (int q = 0; q < S; ++q) {
+                            if constexpr (RS == 2) {
+                                const double2 aa = *reinterpret_cast<const double2 *>(Ai + q * S + r);
+                                acc[0] = fma(aa.x, v[q], acc[0]);
+                                acc[1] = fma(aa.y, v[q], acc[1]);
+                            } else {
+                                acc[0] = fma(Ai[q * S + r], v[q], acc[0]);
+                            }
                         }
-                        Pblk[r * S + sg] = lxx + acc;
+#pragma unroll
+                        for (int e = 0; e < RS; ++e) {
+                            const int rr = r + e;
+                            double lxx = 0.0;
+                            if (i == j) {
+                                const double *Q = bt.Q + cost_row(i) * S * S;
+                                lxx = w_ref * (Q[rr * S + sg] + Q[sg * S + rr]);
+                                if (rr < 3 && sg < 3) lxx += sHd[9 * i + rr * 3 + sg];
+                            } else if (rr < 3 && sg < 3) {
+                                lxx = sHo[9 * pair_index(i, j, a) + rr * 3 + sg];
+                            }
+                            Pblk[rr * S + sg] = lxx + acc[e];
+                        }
                     }
                 }
             }
             tick(2);
+        }
+        __syncthreads();
+        tick(3);
+        // ---- pack the factors in pivot order so the substitutions read contiguous memory (all threads)
+        for (int e = tid; e < m * m; e += nthr) {
+            const int k = e / m, x2 = e - k * m;
+            const double v = W[order[x2] * LDW + k];
+            if (x2 > k) Lp[k * LDF + x2] = v;   // l(x2, k)
+            else Up[k * LDF + x2] = v;          // u(x2, k): column k, row x2 <= k
+            if (x2 == k) {
+                if (!(fabs(v) > 0.0)) st |= DPILQR_ST_SINGULAR;  // exact zero (or NaN) pivot
+                rdiag[k] = __drcp_rn(v);
+            }
+        }
+        if constexpr (USE_MMA) {
+            // The blocked forward solve of phase D applies the 8x8 diagonal blocks of the unit lower factor (well
+            // conditioned: |l| <= 1) as explicit inverses on the tensor path: invert them here, in place.  One
+            // thread per (block, column of the inverse).
+            constexpr int M = AT * C, NB = M / 8;
+            __syncthreads();
+            const int bb = tid >> 3, j = tid & 7;
+            double x[8];
+            const bool busy = tid < NB * 8;
+            if (busy) {
+                const double *F = Lp + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = l(rr, c) of this block
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {  // unit lower: solve L x = e_j by forward substitution
+                    double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int c = 0; c < i; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
+                    x[i] = acc;
+                }
+            }
+            __syncthreads();
+            if (busy) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Lp[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j), same transposed layout
+            }
         }
         __syncthreads();
         tick(5);
@@ -455,7 +492,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
 
         // ---- phase D: K = -Q_uu^{-1} Q_ux, d = -Q_uu^{-1} Q_u.  Right-hand sides 0..n-1 are the columns of Q_ux,
         // right-hand side n is Q_u.  The negated, row-permuted right-hand sides are substituted in place in KB.
-        double *Kt = Kb + (int64_t)t * m * n;
+        double *Kt = p.K + ((int64_t)problem() * T + t) * m * n;
         if constexpr (USE_MMA) {
             constexpr int M = AT * C, NB = M / 8;
             // Blocked triangular solves: each warp owns tiles of 8 right-hand sides and needs no other warp.  Every
@@ -548,7 +585,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         for (int k = tid; k < m; k += nthr) {
             const double dk = KB[(size_t)k * LDN + n];
             dv[k] = dk;
-            db[(int64_t)t * m + k] = dk;
+            p.d[((int64_t)problem() * T + t) * m + k] = dk;
         }
         __syncthreads();
         tick(4);
@@ -691,8 +728,9 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         __syncthreads();
         tick(8);
     }
-    if (timing) {
-        for (int k = 0; k < (tid == 0 ? 12 : 8); ++k) p.timing[(tid == 0 ? 0 : 12) + k] = tacc[k];
+    if (timing && (tid & 31) == 0) {
+        for (int k = 0; k < 12; ++k) p.timing[(tid == 0 ? 0 : 12) + k] = tacc[k];
+        if (tid == 0) p.timing[24] = tacc[24], p.timing[25] = tacc[25], p.timing[26] = tacc[26];
     }
     if (st != 0 && p.status) atomicOr(p.status + b, st);
 }
@@ -719,10 +757,11 @@ int64_t backward_scratch_doubles(int n_problems, int a, int s, int c)
     return plan.use_global_scratch ? (int64_t)n_problems * (int64_t)backward_scratch_per_cta(a * c, a * s) : 0;
 }
 
-template <int S, int C, int AT, bool GLOBAL>
+// TIMED: the instrumented build of the kernel (per-phase cycle counters); the product build carries no timing code
+template <int S, int C, int AT, bool GLOBAL, bool TIMED = false>
 static int launch_typed(const BackwardParams &p, int n_blocks, const BackwardPlan &plan, cudaStream_t stream)
 {
-    auto kernel = backward_kernel<S, C, AT, GLOBAL>;
+    auto kernel = backward_kernel<S, C, AT, GLOBAL, TIMED>;
     static bool attr_set = false;
     if (!attr_set) {
         DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -766,7 +805,10 @@ int launch_backward(const BackwardParams &p_in, int n_blocks, cudaStream_t strea
         return DPILQR_E_INVALID;
     }
     if (s == 12 && c == 4) {
-        if (a == 10 && !plan.use_global_scratch) return launch_typed<12, 4, 10, false>(p, n_blocks, plan, stream);
+        if (a == 10 && !plan.use_global_scratch) {
+            if (p.timing != nullptr) return launch_typed<12, 4, 10, false, true>(p, n_blocks, plan, stream);
+            return launch_typed<12, 4, 10, false>(p, n_blocks, plan, stream);
+        }
         return launch_generic<12, 4>(p, n_blocks, plan, stream);
     }
     if (s == 6 && c == 3) return launch_generic<6, 3>(p, n_blocks, plan, stream);

@@ -194,14 +194,17 @@ __device__ __noinline__ void lu_lookahead(double *__restrict__ W, double *__rest
 //     the pivot rows (28 FMAs, a dependency chain of 7).
 //   * The trailing update A22 -= L21 U12 runs on the FP64 tensor path, 8x8 tiles over all rows with the multipliers
 //     of used rows masked to zero (rows never move).  The column tile of the NEXT panel is updated first so that
-//     warp 0 factorises panel p+1 while warps 1..7 finish the update of panel p (look-ahead).
-template <int M>
+//     warp 0 factorises panel p+1 while the other warps finish the update of panel p (look-ahead).
+// NT threads (gt = 0..NT-1) call this together; they synchronise on named barrier 1.
+template <int M, int NT, bool TIMED = false>
 __device__ __noinline__ void lu_blocked(double *__restrict__ W, int *__restrict__ order, unsigned *__restrict__ donebuf, int gt,
                                         long long *__restrict__ lt)
 {
     static_assert(M % 8 == 0 && M <= 64, "blocked LU: m must be a multiple of 8, at most 64");
     constexpr int LDW = backward_ldw(M);
     constexpr int NP = M / 8;
+    constexpr int NW = NT / 32;  // warps of the group: warp 0 factorises the panels, the others update
+    static_assert(NW >= 2, "blocked LU: at least two warps");
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = gt & 31, warp = gt >> 5;
     const int r0 = lane, r1 = lane + 32;
@@ -212,11 +215,12 @@ __device__ __noinline__ void lu_blocked(double *__restrict__ W, int *__restrict_
     // relative count as tied and the lowest row wins (|l| <= 1 + 2^-13: the stability bound of partial pivoting
     // is unchanged).  A used row has key 0, below every live row (tag bit 64).
     const unsigned tag0 = 64u | (unsigned)(63 - r0), tag1 = 64u | (unsigned)(63 - r1);
-    long long tm = lt ? clock64() : 0;
+    // instrumented build: lt is non-null for every lane of warp 0 (no divergence inside the warp), lane 0 records
+    long long tm = (TIMED && lt) ? clock64() : 0;
     auto lap = [&](int slot) {
-        if (lt) {
+        if (TIMED && lt) {
             const long long now = clock64();
-            lt[slot] += now - tm;
+            if (lane == 0) lt[slot] += now - tm;
             tm = now;
         }
     };
@@ -272,11 +276,11 @@ __device__ __noinline__ void lu_blocked(double *__restrict__ W, int *__restrict_
             const unsigned b0 = __ballot_sync(FULL, done0), b1 = __ballot_sync(FULL, done1);
             if (lane == 0) donebuf[2 * (p & 1)] = b0, donebuf[2 * (p & 1) + 1] = b1;
         }
-        lap(0);
-        named_barrier(1, kSolveThreads);  // panel p and every earlier trailing update are in shared memory
+        lap(p == 0 ? 0 : 2);
+        named_barrier(1, NT);  // panel p and every earlier trailing update are in shared memory
         if (p == NP - 1) break;
         // ---- U12: rows of U right of the panel, one lane per column
-        for (int c = c0 + 8 + gt; c < M; c += kSolveThreads) {
+        for (int c = c0 + 8 + gt; c < M; c += NT) {
             double u[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -290,7 +294,7 @@ __device__ __noinline__ void lu_blocked(double *__restrict__ W, int *__restrict_
             for (int i = 0; i < 8; ++i) W[order[c0 + i] * LDW + c] = u[i];
         }
         lap(1);
-        named_barrier(1, kSolveThreads);
+        named_barrier(1, NT);
         // ---- trailing update on the tensor path
         const unsigned dm0 = donebuf[2 * (p & 1)], dm1 = donebuf[2 * (p & 1) + 1];
         auto tile = [&](int rt, int ct) {
@@ -311,12 +315,12 @@ __device__ __noinline__ void lu_blocked(double *__restrict__ W, int *__restrict_
         };
         const int nct = NP - 1 - p;
         if (warp >= 1) {
-            for (int rt = warp - 1; rt < NP; rt += 7) tile(rt, 0);
+            for (int rt = warp - 1; rt < NP; rt += NW - 1) tile(rt, 0);
         }
-        named_barrier(1, kSolveThreads);  // the columns of panel p+1 are final: warp 0 goes ahead
-        lap(2);
+        named_barrier(1, NT);  // the columns of panel p+1 are final: warp 0 goes ahead
+        lap(1);
         if (warp >= 1) {
-            for (int i = warp - 1; i < NP * (nct - 1); i += 7) tile(i % NP, 1 + i / NP);
+            for (int i = warp - 1; i < NP * (nct - 1); i += NW - 1) tile(i % NP, 1 + i / NP);
         }
     }
 }

@@ -29,10 +29,10 @@ for rep in range(2):
     torch.cuda.synchronize()
 print(f"backward launch: {e0.elapsed_time(e1):.3f} ms for {B} problems (a={a})")
 c = buf.cpu().numpy()
-names = ["load", "phaseA", "LU", "pack", "D-out", "join", "Epre", "E", "F", "regul.", "D-trsm", "prefetch"]
+names = ["load", "phaseA", "LU", "join", "D-out", "pack", "Epre", "E", "F", "regul.", "D-trsm", "prefetch"]
 tot = c[:12].sum()
 for k, nm in enumerate(names):
     print(f"  thread0 {nm:7s} {c[k] / 50:10.0f} cycles/step {100 * c[k] / max(tot, 1):5.1f}%")
 print(f"  group2 phaseB {c[14] / 50:10.0f} cycles/step; total {tot / 50:.0f} cycles/step")
-print(f"  LU detail: panel {c[15] / 50:.0f}  U12+wait {c[16] / 50:.0f}  next-panel tiles+waits {c[17] / 50:.0f} cycles/step")
+print(f"  LU detail: first panel {c[24] / 50:.0f}  U12+tiles+waits {c[25] / 50:.0f}  panels 1..4 {c[26] / 50:.0f} cycles/step")
 _native.lib().dpilqr_debug_backward_timing(None)
