@@ -368,6 +368,9 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid < 32) ? tacc + 24 : nullptr);
             else lu_lookahead<(AT > 0 ? AT * C : 0)>(W, colbuf, rinvbuf, prbuf, order, m, gt);
             tick(2);
+            if constexpr (USE_MMA && TIMED) {  // timing experiment: a second, warm pass over the same code
+                if (p.debug_mode & 4) lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, nullptr);
+            }
         } else if (!idle_group) {
             // ================= group 2: phase B, Q_xx = L_xx + A^T P A in place (upper blocks) =================
             const int gt = USE_MMA ? ((((warp >> 2) - 1) * 3 + (warp & 3) - 1) << 5) + lane : tid - kSolveThreads;

@@ -197,7 +197,7 @@ __device__ __noinline__ void lu_lookahead(double *__restrict__ W, double *__rest
 //     warp 0 factorises panel p+1 while the other warps finish the update of panel p (look-ahead).
 // NT threads (gt = 0..NT-1) call this together; they synchronise on named barrier 1.
 template <int M, int NT, bool TIMED = false>
-__device__ __noinline__ void lu_blocked(double *__restrict__ W, int *__restrict__ order, unsigned *__restrict__ donebuf, int gt,
+__device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restrict__ order, unsigned *__restrict__ donebuf, int gt,
                                         long long *__restrict__ lt)
 {
     static_assert(M % 8 == 0 && M <= 64, "blocked LU: m must be a multiple of 8, at most 64");

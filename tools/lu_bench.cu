@@ -16,7 +16,7 @@ constexpr int M = 40;
 constexpr int LDW = backward_ldw(M);
 
 template <int VARIANT>
-__global__ void __launch_bounds__(512, 1) bench_kernel(const double *A, double *out, int *order_out, long long *cycles, int reps)
+__global__ void __launch_bounds__(512, 1) bench_kernel(const double *A, double *out, int *order_out, long long *cycles, int reps, int park)
 {
     __shared__ __align__(16) double W[M * LDW];
     __shared__ __align__(16) double W0[M * LDW];
@@ -25,8 +25,11 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(const double *A, double *
     __shared__ int order[M];
     extern __shared__ double big[];  // optional ballast: the backward kernel runs with 227 kB carved out
     const int tid = threadIdx.x;
-    if (tid >= 256) {  // optional idle warps, parked like the other warp group of the backward kernel
+    if (tid >= 256) {  // optional idle warps, parked at the CTA barrier like the other warp group of the backward kernel
         if (big[0] == 123.456) cycles[0] = 1;
+        if (park) {
+            for (int r = 0; r < reps; ++r) __syncthreads();
+        }
         return;
     }
     for (int e = tid; e < M * M; e += 256) W0[(e / M) * LDW + e % M] = A[(size_t)blockIdx.x * M * M + e];
@@ -41,6 +44,7 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(const double *A, double *
         else lu_lookahead<M>(W, colbuf, rinvbuf, reinterpret_cast<int *>(rinvbuf + 2), order, M, tid);
         named_barrier(3, 256);
         acc += clock64() - t0;
+        if (park) __syncthreads();
     }
     if (tid == 0) {
         cycles[4 * blockIdx.x] = acc / reps;
@@ -55,6 +59,7 @@ int main(int argc, char **argv)
     const int reps = argc > 1 ? atoi(argv[1]) : 200;
     const int nb = 148;
     std::vector<double> A((size_t)nb * M * M);
+    const int park = argc > 5 ? atoi(argv[5]) : 0;
     const double diag = argc > 4 ? atof(argv[4]) : 2.0;
     srand(1);
     for (int b = 0; b < nb; ++b)
@@ -72,9 +77,9 @@ int main(int argc, char **argv)
     printf("threads %d, dynamic shared memory %zu bytes\n", threads, ballast);
     for (int variant = 0; variant < 3; ++variant) {
         for (int pass = 0; pass < 2; ++pass) {
-            if (variant == 0) bench_kernel<0><<<nb, threads, ballast>>>(dA, dout, dorder, dcyc, reps);
-            else if (variant == 1) bench_kernel<1><<<nb, threads, ballast>>>(dA, dout, dorder, dcyc, reps);
-            else bench_kernel<2><<<nb, threads, ballast>>>(dA, dout, dorder, dcyc, reps);
+            if (variant == 0) bench_kernel<0><<<nb, threads, ballast>>>(dA, dout, dorder, dcyc, reps, park);
+            else if (variant == 1) bench_kernel<1><<<nb, threads, ballast>>>(dA, dout, dorder, dcyc, reps, park);
+            else bench_kernel<2><<<nb, threads, ballast>>>(dA, dout, dorder, dcyc, reps, park);
             if (cudaDeviceSynchronize() != cudaSuccess) {
                 printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
                 return 1;
