@@ -276,9 +276,19 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     __syncthreads();
     prefetch_record(T - 1);
 
+    // Every phase re-derives its thread coordinates from an opaque copy of threadIdx.x: the compiler can then neither
+    // hoist a phase's index arithmetic out of the recursion nor keep it alive across the other phases.  The kernel is
+    // capped at 128 registers, and whatever is live across the LU leaves the panel warp fewer registers to schedule in.
+#define DPILQR_PHASE_IDS                                   \
+    int tid_phase_ = threadIdx.x;                          \
+    asm volatile("" : "+r"(tid_phase_));                   \
+    const int tid = tid_phase_, lane = tid & 31, warp = tid >> 5; \
+    (void)lane, (void)warp;
     if (timing) tmark = clock64();
 #pragma unroll 1
     for (int t = T - 1; t >= 0; --t) {
+        {
+            DPILQR_PHASE_IDS
         // Regularise P in place for phase A (P + mu I, control.py:134-135); the plain diagonal waits in pq (free until
         // phase E) and is put back before phase B, which needs the unregularised P.
         for (int k = (p.debug_mode & 8) ? n : tid; k < n; k += nthr) {
@@ -288,11 +298,14 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             pq[k] = v;
             *pd = v + scal[0];
         }
+        }
         tick(9);
         wait_record();
         __syncthreads();
         tick(0);
 
+        {
+            DPILQR_PHASE_IDS
         // ---- phase A: Q_ux, Q_uu (S = B^T (P + mu I) in registers), Q_u, Q_x
         for (int it = tid; it < a * a * C; it += nthr) {
             const int g = it % C;
@@ -352,9 +365,12 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             for (int r = 0; r < S; ++r) acc = fma(Aj[r * S + sg], pvec[j * S + r], acc);
             Qx[col] = sLx[col] + acc;
         }
+        }
         __syncthreads();
         tick(1);
 
+        {
+            DPILQR_PHASE_IDS
         // Two warp groups run side by side.  Tensor-path kernels split by scheduler: the warps of SM sub-partition 0
         // (warp % 4 == 0) factorise Q_uu -- the panel warp is latency-bound and keeps its FP64 pipe to itself -- while
         // the twelve warps of the other sub-partitions compute Q_xx.  Otherwise: first 256 threads / the rest.
@@ -449,8 +465,11 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             }
             tick(2);
         }
+        }
         __syncthreads();
         tick(3);
+        {
+            DPILQR_PHASE_IDS
         // ---- pack the factors in pivot order so the substitutions read contiguous memory (all threads)
         for (int e = tid; e < m * m; e += nthr) {
             const int k = e / m, x2 = e - k * m;
@@ -487,12 +506,15 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 for (int i = 0; i < 8; ++i) Lp[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j), same transposed layout
             }
         }
+        }
         __syncthreads();
         tick(5);
         // the stage record of this step is dead from here on: fetch the next one behind phases D, E and F
         if (t > 0) prefetch_record(t - 1);
         tick(11);
 
+        {
+            DPILQR_PHASE_IDS
         // ---- phase D: K = -Q_uu^{-1} Q_ux, d = -Q_uu^{-1} Q_u.  Right-hand sides 0..n-1 are the columns of Q_ux,
         // right-hand side n is Q_u.  The negated, row-permuted right-hand sides are substituted in place in KB.
         double *Kt = p.K + ((int64_t)problem() * T + t) * m * n;
@@ -577,8 +599,12 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 }
             }
         }
+        }
         __syncthreads();
         tick(10);
+        {
+            DPILQR_PHASE_IDS
+        double *Kt = p.K + ((int64_t)problem() * T + t) * m * n;
         for (int e = tid; e < m * n; e += nthr) {  // stream K[t] out, coalesced
             const int k = e / n, col = e - k * n;
             const double kv = KB[(size_t)k * LDN + col];
@@ -590,9 +616,12 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             dv[k] = dk;
             p.d[((int64_t)problem() * T + t) * m + k] = dk;
         }
+        }
         __syncthreads();
         tick(4);
 
+        {
+            DPILQR_PHASE_IDS
         // ---- phase E: pq = Q_ux^T d and z = Q_uu d + Q_u (before Q_ux is overwritten), then Y = Q_uu K + 2 Q_ux
         for (int col = tid; col < n + m; col += nthr) {
             if (col < n) {
@@ -608,8 +637,11 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 zv[k] = acc + Qu[k];
             }
         }
+        }
         __syncthreads();
         tick(6);
+        {
+            DPILQR_PHASE_IDS
         if constexpr (USE_MMA) {
             constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
             constexpr int MT = M / 8, NT = N / 8, KS = M / 4;
@@ -634,9 +666,12 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 }
             }
         }
+        }
         __syncthreads();
         tick(7);
 
+        {
+            DPILQR_PHASE_IDS
         // ---- phase F: P <- Q_xx + 1/2 (K^T Y + Y^T K) on upper blocks; p <- Q_x + K^T z + Q_ux^T d
         const double *Y = QUX;
         if constexpr (USE_MMA) {
@@ -727,6 +762,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
 #pragma unroll 4
             for (int k = 0; k < m; ++k) acc = fma(KB[(size_t)k * LDN + col], zv[k], acc);
             pvec[col] = Qx[col] + acc + pq[col];
+        }
         }
         __syncthreads();
         tick(8);
