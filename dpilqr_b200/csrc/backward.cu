@@ -652,10 +652,14 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 double c0 = 2.0 * yp[0], c1 = 2.0 * yp[1];
                 const double *ap = QUU + (8 * mt + fr) * LDQ + fc;
                 const double *bp = KB + (size_t)fc * LD + 8 * nt + fr;
+                double e0 = 0.0, e1 = 0.0;  // second accumulator pair: two independent chains
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(c0, c1, ap[4 * ks], bp[(size_t)4 * ks * LD]);
-                yp[0] = c0;
-                yp[1] = c1;
+                for (int ks = 0; ks < KS; ks += 2) {
+                    dmma_m8n8k4(c0, c1, ap[4 * ks], bp[(size_t)4 * ks * LD]);
+                    if (ks + 1 < KS) dmma_m8n8k4(e0, e1, ap[4 * ks + 4], bp[(size_t)(4 * ks + 4) * LD]);
+                }
+                yp[0] = c0 + e0;
+                yp[1] = c1 + e1;
             }
         } else {
             for (int col = tid; col < n; col += nthr) {
@@ -694,14 +698,16 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     }
                     loaded = ti;
                 }
-                double c0 = 0.0, c1 = 0.0;
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: two independent chains
                 const double *kp = KB + (size_t)fc * LD + 8 * tj + fr;
                 const double *yp = Y + (size_t)fc * LD + 8 * tj + fr;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                     dmma_m8n8k4(c0, c1, ak[ks], yp[(size_t)4 * ks * LD]);  // K^T Y
-                    dmma_m8n8k4(c0, c1, ay[ks], kp[(size_t)4 * ks * LD]);  // Y^T K
+                    dmma_m8n8k4(e0, e1, ay[ks], kp[(size_t)4 * ks * LD]);  // Y^T K
                 }
+                c0 += e0;
+                c1 += e1;
                 const int row = 8 * ti + fr, col = 8 * tj + 2 * fc;
                 const int bi = row / S, bj = col / S;  // S is even here, so the pair (col, col+1) shares a block
                 if (bi <= bj) {
