@@ -6,22 +6,25 @@
 //   phase A   S = B^T (P + mu I)  ->  Q_ux = S A,  Q_uu = L_uu + S B      (S only lives in registers)
 //             Q_u = L_u + B^T p,  Q_x = L_x + A^T p
 //   then two warp groups run concurrently (named barriers):
-//     group 1 (4 warps)   phase C  partial-pivot LU of Q_uu -- the pivoting rule of LAPACK dgetf2
-//                                  (the reference calls np.linalg.solve = dgesv, control.py:141-142),
-//                                  done without row swaps: pivot rows are marked, one barrier per column
-//                         phase D  K = -Q_uu^{-1} Q_ux, d = -Q_uu^{-1} Q_u: one thread per right-hand
-//                                  side, the solution vector in registers, right-looking substitution
-//     group 2 (the rest)  phase B  Q_xx = L_xx + A^T P A, in place on the upper-triangular blocks of P
+//     group 1   phase C  partial-pivot LU of Q_uu without row swaps (pivot rows are marked; the reference calls
+//                        np.linalg.solve = dgesv, control.py:141-142).  Tensor-path kernels: four warps, blocked
+//                        panels of 8 columns factorised in registers by one warp (lu.cuh, lu_blocked); otherwise
+//                        eight warps, unblocked with look-ahead pivot search (lu_lookahead).
+//     group 2   phase B  Q_xx = L_xx + A^T P A, in place on the upper-triangular blocks of P
+//   pack      the factors gathered in pivot order (+ 8x8 inverses of the unit-lower diagonal blocks), all threads
+//   phase D   K = -Q_uu^{-1} Q_ux, d = -Q_uu^{-1} Q_u: blocked triangular solves, one warp per 8 right-hand sides
+//             (tensor path) or one thread per right-hand side (generic sizes)
 //   phase E   pq = Q_ux^T d, z = Q_uu d + Q_u, then Y = Q_uu K + 2 Q_ux (in place over Q_ux)
 //   phase F   P <- Q_xx + 1/2 (K^T Y + Y^T K)   (== the reference's symmetrised
 //             Q_xx + K^T Q_uu K + K^T Q_ux + Q_ux^T K), upper blocks only
 //             p <- Q_x + K^T z + Q_ux^T d
 //
-// The GEMM-shaped phases E and F run on the FP64 tensor path (mma.sync.m8n8k4.f64, "DMMA") when
-// the joint sizes are multiples of 8, otherwise on DFMA register tiles.  P, Q_ux/Y, K, Q_uu and the
-// LU factors stay in shared memory for the whole recursion (about 215 kB for 10 Quadcopter12D agents
-// -> one CTA per SM); only the stage records stream in and K, d stream out.  Problems too large for
-// shared memory keep Q_ux/Y and K in an L2-resident global scratch instead (same code).
+// The GEMM-shaped phases D, E, F and the trailing updates of the LU run on the FP64 tensor path
+// (mma.sync.m8n8k4.f64, "DMMA") when the joint sizes are multiples of 8, otherwise on DFMA register tiles.
+// P, Q_ux/Y, K, Q_uu and the LU factors stay in shared memory for the whole recursion (226.5 kB for 10
+// Quadcopter12D agents -> one CTA per SM); only the stage records stream in (TMA bulk copies, one step ahead)
+// and K, d stream out.  Problems too large for shared memory keep Q_ux/Y, K and the LU matrices in an L2-resident
+// global scratch instead (same code).
 #include "kernels.cuh"
 #include "lu.cuh"
 
