@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     constexpr int PBS = S * S + 2;  // +2 doubles de-alias the banks of consecutive blocks
     constexpr int SAS = S * S + 2, SBS = S * C + 2;
     constexpr bool USE_MMA = (AT > 0) && (S % 2 == 0) && ((AT * S) % 8 == 0) && ((AT * C) % 8 == 0);
+    constexpr bool MMA_A = USE_MMA && S == 12 && C == 4 && AT % 2 == 0;  // phase A on the tensor path
     const int LDQ = m + 4;
     const int LDW = backward_ldw(m);  // row stride of the LU work matrix
     const int LDF = backward_ldf(m);  // row stride of the packed factors
@@ -309,7 +310,73 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
 
         {
             DPILQR_PHASE_IDS
-        // ---- phase A: Q_ux, Q_uu (S = B^T (P + mu I) in registers), Q_u, Q_x
+        // ---- phase A: Q_ux, Q_uu, Q_u, Q_x
+        if constexpr (MMA_A) {
+            // Tensor-path form for 12-state / 4-control agents.  S = B^T (P + mu I) is a [m x n] product whose 8-row
+            // tiles are the rows of two agents: the A operand holds B_i^T of one agent per k-step (zero rows for the
+            // other one), the B operand reads P straight from its upper-block storage (transposed below the
+            // diagonal).  S is staged in the K buffer (K of step t+1 is dead by now); Q_ux = S A and Q_uu = S B then
+            // take their k-steps only from the agents whose columns a tile covers (block-diagonal A, B).
+            constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
+            constexpr int NT = N / 8, MT = M / 8;
+            const int fr = lane >> 2, fc = lane & 3;
+            double *Ssm = KB;
+            for (int tile = warp; tile < MT * NT; tile += nwarp) {
+                const int pr = tile / NT, ct = tile - pr * NT;
+                const int col = 8 * ct + fr;  // column of P this lane feeds
+                const int bj = col / S, cc = col - bj * S;
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 6; ++ks) {
+                    const int ag = 2 * pr + ks / 3;    // agent whose rows of P this k-step covers
+                    const int rr = 4 * (ks % 3) + fc;  // row inside that agent's block
+                    const double av = ((fr >> 2) == ks / 3) ? sB[ag * SBS + rr * C + (fr & 3)] : 0.0;
+                    const double bv = (ag <= bj) ? Pb[(size_t)blk_index(ag, bj) * PBS + rr * S + cc]
+                                                 : Pb[(size_t)blk_index(bj, ag) * PBS + cc * S + rr];
+                    if (ks < 3) dmma_m8n8k4(c0, c1, av, bv);
+                    else dmma_m8n8k4(e0, e1, av, bv);
+                }
+                *reinterpret_cast<double2 *>(Ssm + (size_t)(8 * pr + fr) * LD + 8 * ct + 2 * fc) = make_double2(c0 + e0, c1 + e1);
+            }
+            for (int row = tid; row < m; row += nthr) {  // Q_u = L_u + B^T p
+                const int i = row / C, g = row - i * C;
+                const double *Bi = sB + i * SBS;
+                double acc = 0.0;
+#pragma unroll
+                for (int r = 0; r < S; ++r) acc = fma(Bi[r * C + g], pvec[i * S + r], acc);
+                const double qu = sLu[row] + acc;
+                Qu[row] = qu;
+                QUX[(size_t)row * LDN + n] = qu;  // Q_u rides along as right-hand side n
+            }
+            __syncthreads();
+            for (int q = warp; q < MT * MT; q += nwarp) {  // Q_ux = S A follows in warp group 2, beside the LU
+                {
+                    // Q_uu tile: rows 8 mt.. (agents 2 mt, 2 mt + 1), columns 8 nt.. (agents 2 nt, 2 nt + 1)
+                    const int mt = q / MT, nt = q - mt * MT;
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int ja = 2 * nt + e;
+                        const double *sp = Ssm + (size_t)(8 * mt + fr) * LD + ja * S + fc;
+                        const double *bp = sB + ja * SBS + fc * C + (fr & 3);
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk) {
+                            const double bv = ((fr >> 2) == e) ? bp[4 * kk * C] : 0.0;
+                            dmma_m8n8k4(c0, c1, sp[4 * kk], bv);
+                        }
+                    }
+                    const int row = 8 * mt + fr, colq = 8 * nt + 2 * fc;
+                    const int ir = row / C, g = row - ir * C, ic = colq / C, g2 = colq - ic * C;
+                    if (ir == ic) {  // L_uu of the reference cost, w (R + R^T) (cost.py:85-93)
+                        const double *R = bt.R + cost_row(ir) * C * C;
+                        c0 += scal[1] * (R[g * C + g2] + R[g2 * C + g]);
+                        c1 += scal[1] * (R[g * C + g2 + 1] + R[(g2 + 1) * C + g]);
+                    }
+                    *reinterpret_cast<double2 *>(QUU + row * LDQ + colq) = make_double2(c0, c1);
+                    *reinterpret_cast<double2 *>(W + row * LDW + colq) = make_double2(c0, c1);
+                }
+            }
+        } else {
         for (int it = tid; it < a * a * C; it += nthr) {
             const int g = it % C;
             const int j = (it / C) % a;
@@ -359,6 +426,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 Qu[row] = qu;
                 QUX[(size_t)row * LDN + n] = qu;  // Q_u rides along as right-hand side n
             }
+        }
         }
         for (int col = tid; col < n; col += nthr) {
             const int j = col / S, sg = col - j * S;
@@ -464,6 +532,31 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                             Pblk[rr * S + sg] = lxx + acc[e];
                         }
                     }
+                }
+            }
+            if constexpr (MMA_A) {
+                // Q_ux = S A (L_ux == 0, cost.py:91): only phase D needs it, so it runs here in the shadow of the LU
+                constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
+                constexpr int NT = N / 8, MT = M / 8;
+                const int fr = lane >> 2, fc = lane & 3;
+                const double *Ssm = KB;
+                for (int tile = gt >> 5; tile < MT * NT; tile += gn >> 5) {
+                    // Q_ux tile: rows 8 mt.., columns 8 ct..; L_ux == 0 (cost.py:91)
+                    const int mt = tile / NT, ct = tile - mt * NT;
+                    const int col = 8 * ct + fr;
+                    const int bj = col / S, cc = col - bj * S;
+                    const int j0 = (8 * ct) / S, j1 = (8 * ct + 7) / S;
+                    double c0 = 0.0, c1 = 0.0;
+                    for (int ja = j0; ja <= j1; ++ja) {
+                        const double *sp = Ssm + (size_t)(8 * mt + fr) * LD + ja * S + fc;
+                        const double *ap = sA + ja * SAS + fc * S + cc;
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk) {
+                            const double bv = (ja == bj) ? ap[4 * kk * S] : 0.0;
+                            dmma_m8n8k4(c0, c1, sp[4 * kk], bv);
+                        }
+                    }
+                    *reinterpret_cast<double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * ct + 2 * fc) = make_double2(c0, c1);
                 }
             }
             tick(2);
