@@ -622,60 +622,73 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             const int fr = lane >> 2, fc = lane & 3;
             for (int nt = warp; nt < (n + 8) / 8; nt += nwarp) {
                 double *Xc = KB + 8 * nt;
-                // X = -P Q_ux for this warp's 8 right-hand sides: rows in pivot order, negated (lane = 4 rows x 8 cols)
+                // X = -P Q_ux for this warp's 8 right-hand sides (rows in pivot order, negated), kept in registers as
+                // accumulator fragments for both substitutions: lane = row fr, columns 2 fc and 2 fc + 1 of each block.
+                // Only the block being solved goes through shared memory (it is the B operand of its updates).
+                double2 xc[NB];
 #pragma unroll
-                for (int k0 = 0; k0 < M; k0 += 4) {
-                    const int k = k0 + (lane >> 3), cc = lane & 7;
-                    Xc[(size_t)k * LDN + cc] = -QUX[(size_t)order[k] * LDN + 8 * nt + cc];
+                for (int bq = 0; bq < NB; ++bq) {
+                    const double2 q = *reinterpret_cast<const double2 *>(QUX + (size_t)order[8 * bq + fr] * LDN + 8 * nt + 2 * fc);
+                    xc[bq] = make_double2(-q.x, -q.y);
                 }
-                __syncwarp();
+                // ---- forward substitution with the unit lower factor
 #pragma unroll
-                for (int dir = 0; dir < 2; ++dir) {  // 0: forward with the unit lower factor, 1: backward with the upper
-                    const double *F = dir ? Up : Lp;
-#pragma unroll 1
-                    for (int lvl = 0; lvl < NB; ++lvl) {
-                        const int blk = dir ? NB - 1 - lvl : lvl;
-                        if (dir == 1) {
-                            // Upper factor: the diagonal block is substituted through by lanes 0..7 (one right-hand
-                            // side each).  Its explicit inverse would be one more tensor instruction pair, but U carries
-                            // the conditioning of Q_uu and the inverse costs about a digit of accuracy in K.
-                            if (lane < 8) {
-                                double x[8];
+                for (int blk = 0; blk < NB; ++blk) {
+                    double2 *home = reinterpret_cast<double2 *>(Xc + (size_t)(8 * blk + fr) * LDN + 2 * fc);
+                    *home = xc[blk];
+                    __syncwarp();
+                    double d0 = 0.0, d1 = 0.0;  // X_b <- inv(L_bb) X_b
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) x[j] = Xc[(size_t)(8 * blk + j) * LDN + lane];
-#pragma unroll
-                                for (int j = 7; j >= 0; --j) {
-                                    x[j] *= rdiag[8 * blk + j];
-#pragma unroll
-                                    for (int j2 = 0; j2 < j; ++j2) x[j2] = fma(-F[(8 * blk + j) * LDF + 8 * blk + j2], x[j], x[j2]);
-                                }
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) Xc[(size_t)(8 * blk + j) * LDN + lane] = x[j];
-                            }
-                            __syncwarp();
-                        } else {
-                        double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks)
-                            dmma_m8n8k4(d0, d1, F[(8 * blk + 4 * ks + fc) * LDF + 8 * blk + fr],
-                                        Xc[(size_t)(8 * blk + 4 * ks + fc) * LDN + fr]);
+                    for (int ks = 0; ks < 2; ++ks)
+                        dmma_m8n8k4(d0, d1, Lp[(8 * blk + 4 * ks + fc) * LDF + 8 * blk + fr],
+                                    Xc[(size_t)(8 * blk + 4 * ks + fc) * LDN + fr]);
+                    __syncwarp();
+                    xc[blk] = make_double2(d0, d1);
+                    if (blk + 1 < NB) {
+                        *home = xc[blk];
                         __syncwarp();
-                        *reinterpret_cast<double2 *>(Xc + (size_t)(8 * blk + fr) * LDN + 2 * fc) = make_double2(d0, d1);
+                        double xb[2];
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) xb[ks] = Xc[(size_t)(8 * blk + 4 * ks + fc) * LDN + fr];
+#pragma unroll
+                        for (int b2 = blk + 1; b2 < NB; ++b2)
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks)
+                                dmma_m8n8k4(xc[b2].x, xc[b2].y, -Lp[(8 * blk + 4 * ks + fc) * LDF + 8 * b2 + fr], xb[ks]);
                         __syncwarp();
+                    }
+                }
+                // ---- backward substitution with the upper factor
+#pragma unroll
+                for (int blk = NB - 1; blk >= 0; --blk) {
+                    *reinterpret_cast<double2 *>(Xc + (size_t)(8 * blk + fr) * LDN + 2 * fc) = xc[blk];
+                    __syncwarp();
+                    // The diagonal block is substituted through by lanes 0..7 (one right-hand side each).  Its explicit
+                    // inverse would be one more tensor instruction pair, but U carries the conditioning of Q_uu and
+                    // the inverse costs about a digit of accuracy in K.
+                    if (lane < 8) {
+                        double x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = Xc[(size_t)(8 * blk + j) * LDN + lane];
+#pragma unroll
+                        for (int j = 7; j >= 0; --j) {
+                            x[j] *= rdiag[8 * blk + j];
+#pragma unroll
+                            for (int j2 = 0; j2 < j; ++j2) x[j2] = fma(-Up[(8 * blk + j) * LDF + 8 * blk + j2], x[j], x[j2]);
                         }
 #pragma unroll
-                        for (int o = 1; o < NB; ++o) {
-                            const int b2 = dir ? blk - o : blk + o;
-                            if (b2 >= 0 && b2 < NB) {
-                                double *cp = Xc + (size_t)(8 * b2 + fr) * LDN + 2 * fc;
-                                double2 c2 = *reinterpret_cast<double2 *>(cp);
+                        for (int j = 0; j < 8; ++j) Xc[(size_t)(8 * blk + j) * LDN + lane] = x[j];
+                    }
+                    __syncwarp();
+                    if (blk > 0) {
+                        double xb[2];
 #pragma unroll
-                                for (int ks = 0; ks < 2; ++ks)
-                                    dmma_m8n8k4(c2.x, c2.y, -F[(8 * blk + 4 * ks + fc) * LDF + 8 * b2 + fr],
-                                                Xc[(size_t)(8 * blk + 4 * ks + fc) * LDN + fr]);
-                                *reinterpret_cast<double2 *>(cp) = c2;
-                            }
-                        }
+                        for (int ks = 0; ks < 2; ++ks) xb[ks] = Xc[(size_t)(8 * blk + 4 * ks + fc) * LDN + fr];
+#pragma unroll
+                        for (int b2 = 0; b2 < blk; ++b2)
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks)
+                                dmma_m8n8k4(xc[b2].x, xc[b2].y, -Up[(8 * blk + 4 * ks + fc) * LDF + 8 * b2 + fr], xb[ks]);
                         __syncwarp();
                     }
                 }
@@ -721,16 +734,24 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         // ---- phase E: pq = Q_ux^T d and z = Q_uu d + Q_u (before Q_ux is overwritten), then Y = Q_uu K + 2 Q_ux
         for (int col = tid; col < n + m; col += nthr) {
             if (col < n) {
-                double qd = 0.0;
-#pragma unroll 4
-                for (int k = 0; k < m; ++k) qd = fma(QUX[(size_t)k * LDN + col], dv[k], qd);
-                pq[col] = qd;
+                double q4[4] = {0.0, 0.0, 0.0, 0.0};  // four partial sums: the 40-long chain is pure latency otherwise
+                int k = 0;
+                for (; k + 4 <= m; k += 4) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) q4[e] = fma(QUX[(size_t)(k + e) * LDN + col], dv[k + e], q4[e]);
+                }
+                for (; k < m; ++k) q4[0] = fma(QUX[(size_t)k * LDN + col], dv[k], q4[0]);
+                pq[col] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
             } else {
                 const int k = col - n;
-                double acc = 0.0;
-#pragma unroll 4
-                for (int l = 0; l < m; ++l) acc = fma(QUU[k * LDQ + l], dv[l], acc);
-                zv[k] = acc + Qu[k];
+                double z4[4] = {0.0, 0.0, 0.0, 0.0};
+                int l = 0;
+                for (; l + 4 <= m; l += 4) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) z4[e] = fma(QUU[k * LDQ + l + e], dv[l + e], z4[e]);
+                }
+                for (; l < m; ++l) z4[0] = fma(QUU[k * LDQ + l], dv[l], z4[0]);
+                zv[k] = ((z4[0] + z4[1]) + (z4[2] + z4[3])) + Qu[k];
             }
         }
         }
@@ -860,10 +881,17 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             }
         }
         for (int col = tid; col < n; col += nthr) {
-            double acc = 0.0;
-#pragma unroll 4
-            for (int k = 0; k < m; ++k) acc = fma(KB[(size_t)k * LDN + col], zv[k], acc);
-            pvec[col] = Qx[col] + acc + pq[col];
+            double a4[4] = {0.0, 0.0, 0.0, 0.0};
+            int k = 0;
+            for (; k + 4 <= m; k += 4) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a4[e] = fma(KB[(size_t)(k + e) * LDN + col], zv[k + e], a4[e]);
+            }
+            for (; k < m; ++k) a4[0] = fma(KB[(size_t)k * LDN + col], zv[k], a4[0]);
+            const double acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+            const double pnew = Qx[col] + acc + pq[col];
+            if (!isfinite(pnew)) st |= DPILQR_ST_NONFINITE;
+            pvec[col] = pnew;
         }
         }
         __syncthreads();
