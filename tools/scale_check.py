@@ -1,3 +1,5 @@
+#!/usr/bin/env python
+"""Resident solve throughput of the Quad12D batch at several batch sizes (GPU box): tail/quantisation check."""
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
 import dpilqr_b200 as dp
