@@ -279,49 +279,48 @@ __device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restri
         lap(p == 0 ? 0 : 2);
         named_barrier(1, NT);  // panel p and every earlier trailing update are in shared memory
         if (p == NP - 1) break;
-        // ---- U12: rows of U right of the panel, one lane per column
-        for (int c = c0 + 8 + gt; c < M; c += NT) {
-            double u[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const double *row = W + order[c0 + i] * LDW;
-                double acc = row[c];
-#pragma unroll
-                for (int j = 0; j < i; ++j) acc = fma(-row[c0 + j], u[j], acc);
-                u[i] = acc;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) W[order[c0 + i] * LDW + c] = u[i];
-        }
-        lap(1);
-        named_barrier(1, NT);
-        // ---- trailing update on the tensor path
+        // ---- trailing columns: every warp owns whole column tiles -- U12 of the eight columns by lanes 0..7 (the
+        // 8-step forward substitution with the panel's unit-lower block on the pivot rows: 28 FMAs, a chain of 7),
+        // then the update of all row tiles on the tensor path.  Warp 0 takes the columns of the next panel and goes
+        // straight on to factorise it (look-ahead): one barrier per panel.
         const unsigned dm0 = donebuf[2 * (p & 1)], dm1 = donebuf[2 * (p & 1) + 1];
-        auto tile = [&](int rt, int ct) {
-            const int row = 8 * rt + (lane >> 2);
-            const bool rdone = ((row < 32 ? (dm0 >> row) : (dm1 >> (row - 32))) & 1u) != 0;
-            const int col0 = c0 + 8 + 8 * ct;
-            double2 *cptr = reinterpret_cast<double2 *>(W + row * LDW + col0 + 2 * (lane & 3));
-            double2 cv = *cptr;
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const int k = 4 * kk + (lane & 3);
-                const double lv = W[row * LDW + c0 + k];
-                const double av = rdone ? 0.0 : -lv;
-                const double bv = W[order[c0 + k] * LDW + col0 + (lane >> 2)];
-                dmma_m8n8k4(cv.x, cv.y, av, bv);
-            }
-            *cptr = cv;
-        };
         const int nct = NP - 1 - p;
-        if (warp >= 1) {
-            for (int rt = warp - 1; rt < NP; rt += NW - 1) tile(rt, 0);
+        for (int ct = warp; ct < nct; ct += (warp == 0 ? nct : NW - 1)) {
+            const int col0 = c0 + 8 + 8 * ct;
+            if (lane < 8) {
+                const int c = col0 + lane;
+                double u[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const double *row = W + order[c0 + i] * LDW;
+                    double acc = row[c];
+#pragma unroll
+                    for (int j = 0; j < i; ++j) acc = fma(-row[c0 + j], u[j], acc);
+                    u[i] = acc;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) W[order[c0 + i] * LDW + c] = u[i];
+            }
+            __syncwarp();
+            double bv[2];  // rows of U12: the B operand of every row tile
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) bv[kk] = W[order[c0 + 4 * kk + (lane & 3)] * LDW + col0 + (lane >> 2)];
+#pragma unroll
+            for (int rt = 0; rt < NP; ++rt) {
+                const int row = 8 * rt + (lane >> 2);
+                const bool rdone = ((row < 32 ? (dm0 >> row) : (dm1 >> (row - 32))) & 1u) != 0;
+                double2 *cptr = reinterpret_cast<double2 *>(W + row * LDW + col0 + 2 * (lane & 3));
+                double2 cv = *cptr;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const double lv = W[row * LDW + c0 + 4 * kk + (lane & 3)];
+                    dmma_m8n8k4(cv.x, cv.y, rdone ? 0.0 : -lv, bv[kk]);  // multipliers of used rows masked
+                }
+                *cptr = cv;
+            }
+            __syncwarp();
         }
-        named_barrier(1, NT);  // the columns of panel p+1 are final: warp 0 goes ahead
         lap(1);
-        if (warp >= 1) {
-            for (int i = warp - 1; i < NP * (nct - 1); i += NW - 1) tile(i % NP, 1 + i / NP);
-        }
     }
 }
 
