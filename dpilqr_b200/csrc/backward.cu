@@ -201,11 +201,11 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
     };
-    auto prefetch_record = [&](int t) {  // call after a __syncthreads(): nobody reads the previous record any more
+    auto prefetch_record = [&](int t, int issuer = 0) {  // call after a __syncthreads(): nobody reads the previous record any more
         const double *rec = p.stage + ((int64_t)problem() * (T + 1) + t) * L.stride;
         if constexpr (BULK) {
             // the shared-memory home sA | sB | sLx.. mirrors the record layout (common.cuh): one bulk copy
-            if (tid == 0) {
+            if ((int)threadIdx.x == issuer) {
                 const unsigned total = (unsigned)(L.stride * 8);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
@@ -605,8 +605,6 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         }
         __syncthreads();
         tick(5);
-        // the stage record of this step is dead from here on: fetch the next one behind phases D, E and F
-        if (t > 0) prefetch_record(t - 1);
         tick(11);
 
         {
@@ -714,11 +712,20 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         {
             DPILQR_PHASE_IDS
         double *Kt = p.K + ((int64_t)problem() * T + t) * m * n;
-        for (int e = tid; e < m * n; e += nthr) {  // stream K[t] out, coalesced
-            const int k = e / n, col = e - k * n;
-            const double kv = KB[(size_t)k * LDN + col];
-            if (!isfinite(kv)) st |= DPILQR_ST_NONFINITE;
-            Kt[e] = kv;
+        if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(p.K) & 15) == 0) {  // stream K[t] out, coalesced, two entries per access
+            for (int e = tid; e < (m * n) >> 1; e += nthr) {
+                const int k = (2 * e) / n, col = 2 * e - k * n;
+                const double2 kv = *reinterpret_cast<const double2 *>(KB + (size_t)k * LDN + col);
+                if (!isfinite(kv.x) || !isfinite(kv.y)) st |= DPILQR_ST_NONFINITE;
+                *reinterpret_cast<double2 *>(Kt + 2 * e) = kv;
+            }
+        } else {
+            for (int e = tid; e < m * n; e += nthr) {
+                const int k = e / n, col = e - k * n;
+                const double kv = KB[(size_t)k * LDN + col];
+                if (!isfinite(kv)) st |= DPILQR_ST_NONFINITE;
+                Kt[e] = kv;
+            }
         }
         for (int k = tid; k < m; k += nthr) {
             const double dk = KB[(size_t)k * LDN + n];
@@ -731,6 +738,9 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
 
         {
             DPILQR_PHASE_IDS
+        // The stage record of this step has been dead since the warp groups joined: fetch the next one behind phases E
+        // and F.  The last thread issues the copies -- its warp has nothing to do in the vector phase below.
+        if (t > 0) prefetch_record(t - 1, nthr - 1);
         // ---- phase E: pq = Q_ux^T d and z = Q_uu d + Q_u (before Q_ux is overwritten), then Y = Q_uu K + 2 Q_ux
         for (int col = tid; col < n + m; col += nthr) {
             if (col < n) {
