@@ -288,9 +288,28 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     asm volatile("" : "+r"(tid_phase_));                   \
     const int tid = tid_phase_, lane = tid & 31, warp = tid >> 5; \
     (void)lane, (void)warp;
+    auto lu_experiment = [&](int slot) {  // timing experiment: the LU on its own on a synthetic matrix (clobbers W, order)
+        if constexpr (TIMED && USE_MMA) {
+            for (int k = threadIdx.x; k < m * LDW; k += nthr) W[k] = (k % (LDW + 1) == 0) ? 2.0 : 0.001 * ((k * 37) % 101);
+            __syncthreads();
+            long long best = 1ll << 60;
+            for (int rep = 0; rep < 4; ++rep) {
+                __syncthreads();
+                const long long q0 = clock64();
+                if (threadIdx.x < 128)
+                    lu_blocked<AT * C, 128, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), threadIdx.x, nullptr);
+                __syncthreads();
+                const long long q1 = clock64() - q0;
+                best = q1 < best ? q1 : best;
+            }
+            if (blockIdx.x == 0 && threadIdx.x == 0) p.timing[slot] = best;
+        }
+    };
+    if (p.debug_mode & 32) lu_experiment(27);
     if (timing) tmark = clock64();
 #pragma unroll 1
     for (int t = T - 1; t >= 0; --t) {
+        if ((p.debug_mode & 256) && t == T - 1) lu_experiment(28);
         {
             DPILQR_PHASE_IDS
         // Regularise P in place for phase A (P + mu I, control.py:134-135); the plain diagonal waits in pq (free until
@@ -437,6 +456,13 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             Qx[col] = sLx[col] + acc;
         }
         }
+        if constexpr (TIMED) {
+            if (p.debug_mode & 64) {  // experiment: factorise a synthetic matrix instead of Q_uu (wrong numerics)
+                __syncthreads();
+                for (int k = threadIdx.x; k < m * LDW; k += nthr) W[k] = (k % (LDW + 1) == 0) ? 2.0 : 0.001 * ((k * 37) % 101);
+            }
+        }
+        if ((p.debug_mode & 512) && t == T - 2) { __syncthreads(); lu_experiment(29); }
         __syncthreads();
         tick(1);
 
@@ -814,24 +840,16 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             int ti = 0, rowstart = 0;  // decode q0 -> (ti, tj) in the row-major upper triangle of tiles
             while (q0 >= rowstart + (NT - ti)) { rowstart += NT - ti; ++ti; }
             int tj = ti + (q0 - rowstart);
-            double ak[KS], ay[KS];
-            int loaded = -1;
             for (int q = q0; q < q1; ++q) {
-                if (loaded != ti) {
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        ak[ks] = KB[(size_t)(4 * ks + fc) * LD + 8 * ti + fr];
-                        ay[ks] = Y[(size_t)(4 * ks + fc) * LD + 8 * ti + fr];
-                    }
-                    loaded = ti;
-                }
                 double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: two independent chains
                 const double *kp = KB + (size_t)fc * LD + 8 * tj + fr;
                 const double *yp = Y + (size_t)fc * LD + 8 * tj + fr;
+                const double *kq = KB + (size_t)fc * LD + 8 * ti + fr;
+                const double *yq = Y + (size_t)fc * LD + 8 * ti + fr;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    dmma_m8n8k4(c0, c1, ak[ks], yp[(size_t)4 * ks * LD]);  // K^T Y
-                    dmma_m8n8k4(e0, e1, ay[ks], kp[(size_t)4 * ks * LD]);  // Y^T K
+                    dmma_m8n8k4(c0, c1, kq[(size_t)4 * ks * LD], yp[(size_t)4 * ks * LD]);  // K^T Y
+                    dmma_m8n8k4(e0, e1, yq[(size_t)4 * ks * LD], kp[(size_t)4 * ks * LD]);  // Y^T K
                 }
                 c0 += e0;
                 c1 += e1;

@@ -239,26 +239,42 @@ __device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restri
                     y[2 * q] = v1.x, y[2 * q + 1] = v1.y;
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            // The column loop is software-pipelined by hand (the compiler keeps the source order inside the register-
+            // starved recursion loop): the pivot search of column j+1 -- key, speculative reciprocal, warp maximum --
+            // is issued as soon as that one column has been updated, and the rest of the rank-1 update runs in its
+            // shadow; the pivot-row shuffles of a column are issued as one batch.
+            unsigned kmax;
+            double rinv_mine;
+            auto search = [&](int j) {  // |x[j]|, |y[j]| of the unused rows -> warp maximum of the keys
                 const unsigned key0 = done0 ? 0u : (((unsigned)__double2hiint(x[j]) & 0x7fffff80u) | tag0);
                 const unsigned key1 = done1 ? 0u : (((unsigned)__double2hiint(y[j]) & 0x7fffff80u) | tag1);
-                const double rinv_mine = fast_rcp(key1 > key0 ? y[j] : x[j]);  // speculative: only the winner's is used
-                const unsigned kmax = __reduce_max_sync(FULL, max(key0, key1));
+                rinv_mine = fast_rcp(key1 > key0 ? y[j] : x[j]);  // speculative: only the winner's is used
+                kmax = __reduce_max_sync(FULL, max(key0, key1));
+            };
+            search(0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
                 const int pr = 63 - (int)(kmax & 63u);  // warp-uniform
                 const int win = pr & 31;
                 const bool second = pr >= 32;
                 const double rinv = __shfl_sync(FULL, rinv_mine, win);
+                double pv[8];
+#pragma unroll
+                for (int jj = j + 1; jj < 8; ++jj) pv[jj] = __shfl_sync(FULL, second ? y[jj] : x[jj], win);
                 if (lane == 0) order[c0 + j] = pr;
                 done0 = done0 || (pr == r0);
                 done1 = done1 || (pr == r1);
                 // multipliers: zero for used rows, so the updates below need no predicate
                 const double m0 = done0 ? 0.0 : x[j] * rinv, m1 = done1 ? 0.0 : y[j] * rinv;
+                if (j + 1 < 8) {
+                    x[j + 1] = fma(-m0, pv[j + 1], x[j + 1]);
+                    y[j + 1] = fma(-m1, pv[j + 1], y[j + 1]);
+                    search(j + 1);
+                }
 #pragma unroll
-                for (int jj = j + 1; jj < 8; ++jj) {
-                    const double pv = __shfl_sync(FULL, second ? y[jj] : x[jj], win);
-                    x[jj] = fma(-m0, pv, x[jj]);
-                    y[jj] = fma(-m1, pv, y[jj]);
+                for (int jj = j + 2; jj < 8; ++jj) {
+                    x[jj] = fma(-m0, pv[jj], x[jj]);
+                    y[jj] = fma(-m1, pv[jj], y[jj]);
                 }
                 if (!done0) x[j] = m0;
                 if (!done1) y[j] = m1;
