@@ -494,6 +494,102 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 Pb[(size_t)blk_index(i, i) * PBS + r * S + r] = pq[k];
             }
             named_barrier(2, gn);
+            tick(3);
+            if constexpr (MMA_A) {
+                // Tensor-path form: every warp owns whole blocks.  V = P_ij A_j in four 8x8 accumulator tiles (the
+                // 12x12 block padded to 16x16: rows/columns 12..15 are zero operands), V written over P_ij (the block is
+                // consumed), then Q = A_i^T V with V as the B operand, and L_xx added in the epilogue.  No barrier:
+                // a block is read and written by one warp only.
+                const int fr = lane >> 2, fc = lane & 3;
+                const double w_ref = scal[1];
+                for (int blk = (p.debug_mode & 16) ? nblk : (gt >> 5); blk < nblk; blk += gn >> 5) {
+                    int i = 0, rem = blk;
+                    while (rem >= a - i) { rem -= a - i; ++i; }
+                    const int j = i + rem;
+                    double *Pblk = Pb + (size_t)blk * PBS;
+                    const double *Ai = sA + i * SAS, *Aj = sA + j * SAS;
+                    const bool diag = (i == j);
+                    // L_xx of the reference cost, w (Q + Q^T) (cost.py:85-93), on diagonal blocks: loads issued up front
+                    double lq[2][2][2];
+                    const double *Qref = bt.Q + (diag ? cost_row(i) : 0) * S * S;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int r = 8 * mt + fr, cc = 8 * nt + 2 * fc + e;
+                                lq[mt][nt][e] = 0.0;
+                                if (diag && r < S && cc < S) lq[mt][nt][e] = Qref[r * S + cc] + Qref[cc * S + r];
+                            }
+                    // k-steps outermost: the tensor instructions are volatile asm and issue in program order, so the four
+                    // independent tiles have to be interleaved by hand
+                    double2 acc[2][2];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) acc[mt][nt] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int ks = 0; ks < S / 4; ++ks) {
+                        double av[2], bv[2];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            av[h] = (8 * h + fr < S) ? Pblk[(8 * h + fr) * S + 4 * ks + fc] : 0.0;
+                            bv[h] = (8 * h + fr < S) ? Aj[(4 * ks + fc) * S + 8 * h + fr] : 0.0;
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) dmma_m8n8k4(acc[mt][nt].x, acc[mt][nt].y, av[mt], bv[nt]);
+                    }
+                    __syncwarp();  // every lane has read P_ij: overwrite it with V
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const int r = 8 * mt + fr, cc = 8 * nt + 2 * fc;
+                            if (r < S && cc < S) *reinterpret_cast<double2 *>(Pblk + r * S + cc) = acc[mt][nt];
+                        }
+                    __syncwarp();
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) acc[mt][nt] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int ks = 0; ks < S / 4; ++ks) {
+                        double av[2], bv[2];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            av[h] = (8 * h + fr < S) ? Ai[(4 * ks + fc) * S + 8 * h + fr] : 0.0;
+                            bv[h] = (8 * h + fr < S) ? Pblk[(4 * ks + fc) * S + 8 * h + fr] : 0.0;
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) dmma_m8n8k4(acc[mt][nt].x, acc[mt][nt].y, av[mt], bv[nt]);
+                    }
+                    __syncwarp();  // V has been consumed: overwrite it with Q_xx
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const int r = 8 * mt + fr, cc = 8 * nt + 2 * fc;
+                            if (r < S && cc < S) {
+                                double out[2] = {acc[mt][nt].x, acc[mt][nt].y};
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    double lxx = diag ? w_ref * lq[mt][nt][e] : 0.0;
+                                    if (r < 3 && cc + e < 3) {  // the proximity Hessians only touch the 3x3 position corner
+                                        if (diag) lxx += sHd[9 * i + r * 3 + cc + e];
+                                        else lxx = sHo[9 * pair_index(i, j, a) + r * 3 + cc + e];
+                                    }
+                                    out[e] = lxx + out[e];
+                                }
+                                *reinterpret_cast<double2 *>(Pblk + r * S + cc) = make_double2(out[0], out[1]);
+                            }
+                        }
+                }
+            } else {
             for (int blk0 = (p.debug_mode & 16) ? nblk : 0; blk0 < nblk; blk0 += blocks_per_round) {
                 const int blk = blk0 + gt / S;
                 const int sg = gt % S;
@@ -560,13 +656,18 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     }
                 }
             }
+            }
+            tick(4);
+            tick(2);
+        } else {
             if constexpr (MMA_A) {
-                // Q_ux = S A (L_ux == 0, cost.py:91): only phase D needs it, so it runs here in the shadow of the LU
+                // Q_ux = S A (L_ux == 0, cost.py:91): only phase D needs it, so it runs in the shadow of the LU -- on the
+                // three warps that share the panel warp's scheduler (short enough not to hold the panel up for long)
                 constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
                 constexpr int NT = N / 8, MT = M / 8;
                 const int fr = lane >> 2, fc = lane & 3;
                 const double *Ssm = KB;
-                for (int tile = gt >> 5; tile < MT * NT; tile += gn >> 5) {
+                for (int tile = (warp >> 2) - 1; tile < MT * NT; tile += 3) {
                     // Q_ux tile: rows 8 mt.., columns 8 ct..; L_ux == 0 (cost.py:91)
                     const int mt = tile / NT, ct = tile - mt * NT;
                     const int col = 8 * ct + fr;
@@ -585,7 +686,6 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     *reinterpret_cast<double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * ct + 2 * fc) = make_double2(c0, c1);
                 }
             }
-            tick(2);
         }
         }
         __syncthreads();

@@ -47,6 +47,7 @@ tot = c[:12].sum()
 for k, nm in enumerate(names):
     print(f"  thread0 {nm:7s} {c[k] / 50:10.0f} cycles/step {100 * c[k] / max(tot, 1):5.1f}%")
 print(f"  group2 phaseB {c[14] / 50:10.0f} cycles/step; total {tot / 50:.0f} cycles/step")
+print(f"  group 2 detail: restore+barrier {c[15] / 50:.0f}  Q_xx blocks {c[16] / 50:.0f}  Q_ux tiles {c[14] / 50:.0f} cycles/step")
 print(f"  LU detail: first panel {c[24] / 50:.0f}  U12+tiles+waits {c[25] / 50:.0f}  panels 1..4 {c[26] / 50:.0f} cycles/step")
 print(f"  LU experiment (debug modes 32/256/512): before the recursion {c[27]}, top of the first step {c[28]}, after phase A of the second step {c[29]} cycles")
 _native.lib().dpilqr_debug_backward_timing(None)
