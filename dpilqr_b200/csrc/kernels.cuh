@@ -53,7 +53,9 @@ struct BackwardParams {
     double *scratch;  // global scratch for the big-problem path (2*m*n doubles per CTA)
     int use_global_scratch;
     long long *timing;  // optional: 20 per-phase cycle counters written by CTA 0 (debug aid)
-    int debug_mode;     // timing experiments only (wrong numerics): 1 no pivot search, 2 no elimination, 4 no keys
+    int debug_mode;     // timing experiments of the instrumented build only (wrong numerics), env DPILQR_DEBUG_BACKWARD_MODE:
+                        // 4 a second LU call, 8 no regularisation pass, 16 no Q_xx, 64 LU of a synthetic matrix,
+                        // 32 / 256 / 512 the LU alone before the recursion / at the top of / inside a step
 };
 extern long long *g_backward_timing;
 extern int g_backward_debug_mode;

@@ -215,10 +215,10 @@ int64_t dpilqr_solve_batch_host(const dpilqr_batch *host_batch, const dpilqr_sol
                                 double *trace_J, int device);
 /* copy (and optionally reset) the accumulated per-kernel timings of solves run with opts->profile = 1 */
 int dpilqr_get_profile(dpilqr_profile *out, int reset);
-/* Debug aid: when set to a device buffer of 32 int64, CTA 0 of every backward launch writes its per-phase
- * cycle counts there (slots 0..11: thread 0; slots 12..19: first thread of the Q_xx warp group) and CTA 0 of
- * every rollout / line-search launch writes slots 24..29 (see tools/backward_phases.py, tools/forward_phases.py).
- * NULL switches it off. */
+/* Debug aid: when set to a device buffer of 32 int64, backward launches run the instrumented build of the kernel
+ * and CTA 0 writes its per-phase cycle counts there (slots 0..11: warp 0; 12..23: first warp of the Q_xx group;
+ * 24..29: LU detail and experiments); CTA 0 of every rollout / line-search launch writes slots 24..29 (see
+ * tools/backward_phases.py, tools/forward_phases.py).  NULL switches it off. */
 int dpilqr_debug_backward_timing(long long *device_counters);
 /* release the cached device memory of dpilqr_solve_batch_host */
 int dpilqr_release_cache(void);
