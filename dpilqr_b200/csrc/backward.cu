@@ -477,6 +477,38 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         if (lu_group) {
             // ================= group 1: phase C, LU with implicit partial pivoting =================
             const int gt = tid;
+            if constexpr (MMA_A) {
+                // Q_ux = S A (L_ux == 0, cost.py:91): only phase D needs it, so it runs in the shadow of the LU: the three
+                // update warps of the LU group do it while warp 0 factorises the first panel (they have nothing else to do
+                // until then); the warps that share the panel warp's scheduler stay parked
+                constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
+                constexpr int NT = N / 8, MT = M / 8;
+                const int fr = lane >> 2, fc = lane & 3;
+                const double *Ssm = KB;
+                // a warp takes whole column tiles: the A_j operand is shared by the MT row tiles, whose independent
+                // accumulator chains keep the tensor pipe busy -- these warps are due back at the first trailing update
+                for (int ct = (gt >> 5) - 1; ct < NT && (gt >> 5) >= 1; ct += 3) {
+                    const int col = 8 * ct + fr;
+                    const int bj = col / S, cc = col - bj * S;
+                    const int j0 = (8 * ct) / S, j1 = (8 * ct + 7) / S;
+                    double2 acc[MT];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) acc[mt] = make_double2(0.0, 0.0);
+                    for (int ja = j0; ja <= j1; ++ja) {
+                        const double *sp = Ssm + (size_t)fr * LD + ja * S + fc;
+                        const double *ap = sA + ja * SAS + fc * S + cc;
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk) {
+                            const double bv = (ja == bj) ? ap[4 * kk * S] : 0.0;
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) dmma_m8n8k4(acc[mt].x, acc[mt].y, sp[(size_t)8 * mt * LD + 4 * kk], bv);
+                        }
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        *reinterpret_cast<double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * ct + 2 * fc) = acc[mt];
+                }
+            }
             if constexpr (USE_MMA)
                 lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid < 32) ? tacc + 24 : nullptr);
             else lu_lookahead<(AT > 0 ? AT * C : 0)>(W, colbuf, rinvbuf, prbuf, order, m, gt);
@@ -659,33 +691,6 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             }
             tick(4);
             tick(2);
-        } else {
-            if constexpr (MMA_A) {
-                // Q_ux = S A (L_ux == 0, cost.py:91): only phase D needs it, so it runs in the shadow of the LU -- on the
-                // three warps that share the panel warp's scheduler (short enough not to hold the panel up for long)
-                constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
-                constexpr int NT = N / 8, MT = M / 8;
-                const int fr = lane >> 2, fc = lane & 3;
-                const double *Ssm = KB;
-                for (int tile = (warp >> 2) - 1; tile < MT * NT; tile += 3) {
-                    // Q_ux tile: rows 8 mt.., columns 8 ct..; L_ux == 0 (cost.py:91)
-                    const int mt = tile / NT, ct = tile - mt * NT;
-                    const int col = 8 * ct + fr;
-                    const int bj = col / S, cc = col - bj * S;
-                    const int j0 = (8 * ct) / S, j1 = (8 * ct + 7) / S;
-                    double c0 = 0.0, c1 = 0.0;
-                    for (int ja = j0; ja <= j1; ++ja) {
-                        const double *sp = Ssm + (size_t)(8 * mt + fr) * LD + ja * S + fc;
-                        const double *ap = sA + ja * SAS + fc * S + cc;
-#pragma unroll
-                        for (int kk = 0; kk < 3; ++kk) {
-                            const double bv = (ja == bj) ? ap[4 * kk * S] : 0.0;
-                            dmma_m8n8k4(c0, c1, sp[4 * kk], bv);
-                        }
-                    }
-                    *reinterpret_cast<double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * ct + 2 * fc) = make_double2(c0, c1);
-                }
-            }
         }
         }
         __syncthreads();
