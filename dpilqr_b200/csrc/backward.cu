@@ -945,20 +945,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             int ti = 0, rowstart = 0;  // decode q0 -> (ti, tj) in the row-major upper triangle of tiles
             while (q0 >= rowstart + (NT - ti)) { rowstart += NT - ti; ++ti; }
             int tj = ti + (q0 - rowstart);
-            for (int q = q0; q < q1; ++q) {
-                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: two independent chains
-                const double *kp = KB + (size_t)fc * LD + 8 * tj + fr;
-                const double *yp = Y + (size_t)fc * LD + 8 * tj + fr;
-                const double *kq = KB + (size_t)fc * LD + 8 * ti + fr;
-                const double *yq = Y + (size_t)fc * LD + 8 * ti + fr;
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    dmma_m8n8k4(c0, c1, kq[(size_t)4 * ks * LD], yp[(size_t)4 * ks * LD]);  // K^T Y
-                    dmma_m8n8k4(e0, e1, yq[(size_t)4 * ks * LD], kp[(size_t)4 * ks * LD]);  // Y^T K
-                }
-                c0 += e0;
-                c1 += e1;
-                const int row = 8 * ti + fr, col = 8 * tj + 2 * fc;
+            auto add_tile = [&](int tr, int tc, double c0, double c1) {  // P tile (tr, tc) += 1/2 (c0, c1)
+                const int row = 8 * tr + fr, col = 8 * tc + 2 * fc;
                 const int bi = row / S, bj = col / S;  // S is even here, so the pair (col, col+1) shares a block
                 if (bi <= bj) {
                     double *pblk = Pb + (size_t)blk_index(bi, bj) * PBS;
@@ -967,12 +955,43 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     pblk[rr * S + cc + 1] += 0.5 * c1;
                     // diagonal blocks are stored in full: an off-diagonal tile inside one also owns the mirrored
                     // entries (their own tile lies below the tile diagonal and is never visited)
-                    if (bi == bj && ti != tj) {
+                    if (bi == bj && tr != tc) {
                         pblk[cc * S + rr] += 0.5 * c0;
                         pblk[(cc + 1) * S + rr] += 0.5 * c1;
                     }
                 }
-                if (++tj == NT) { ++ti; tj = ti; }
+            };
+            for (int q = q0; q < q1;) {
+                // Two neighbouring tiles of a tile row share the row's operand fragments (K^T and Y^T of rows 8 ti..):
+                // six shared-memory loads for four tensor instructions instead of eight, four independent chains.
+                const bool two = (q + 1 < q1) && (tj + 1 < NT);
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+                const double *kp = KB + (size_t)fc * LD + 8 * tj + fr;
+                const double *yp = Y + (size_t)fc * LD + 8 * tj + fr;
+                const double *kq = KB + (size_t)fc * LD + 8 * ti + fr;
+                const double *yq = Y + (size_t)fc * LD + 8 * ti + fr;
+                if (two) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const double ak = kq[(size_t)4 * ks * LD], ay = yq[(size_t)4 * ks * LD];
+                        dmma_m8n8k4(c0, c1, ak, yp[(size_t)4 * ks * LD]);      // K^T Y
+                        dmma_m8n8k4(e0, e1, ay, kp[(size_t)4 * ks * LD]);      // Y^T K
+                        dmma_m8n8k4(g0, g1, ak, yp[(size_t)4 * ks * LD + 8]);  // same for the next column tile
+                        dmma_m8n8k4(h0, h1, ay, kp[(size_t)4 * ks * LD + 8]);
+                    }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        dmma_m8n8k4(c0, c1, kq[(size_t)4 * ks * LD], yp[(size_t)4 * ks * LD]);
+                        dmma_m8n8k4(e0, e1, yq[(size_t)4 * ks * LD], kp[(size_t)4 * ks * LD]);
+                    }
+                }
+                add_tile(ti, tj, c0 + e0, c1 + e1);
+                if (two) add_tile(ti, tj + 1, g0 + h0, g1 + h1);
+                const int step = two ? 2 : 1;
+                q += step;
+                tj += step;
+                if (tj >= NT) { ++ti; tj = ti; }
             }
         } else {
             constexpr int TS = TileSize<S>::value;
