@@ -159,7 +159,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one backward launch over 3908 problems (profiles/r01_backward_ncu_full.txt)
-NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM = (4.180452e9 + 7.518299e9) / 3908
+NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM = (4.180168e9 + 7.515227e9) / 3908
 
 
 def measure_fp64_peak():
@@ -282,7 +282,7 @@ def run_gpu_arm(args):
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM * bunits / max(blaunch, 1),
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum = 11.699 GB for a 3908-problem launch "
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum = 11.695 GB for a 3908-problem launch "
                                            "(profiles/r01_backward_ncu_full.txt), scaled to this run's average problems per launch; "
                                            "algorithmic bytes/problem = %d" % backward_hbm_bytes(),
                          "peak_source": peak_src,
