@@ -147,12 +147,21 @@ __global__ void __launch_bounds__(128) linquad_kernel(const LinQuadParams p)
         if (!terminal) {
             double *A = rec + L.offA + i * L.strideA;
             double *Bm = rec + L.offB + i * L.strideB;
+            if constexpr ((NX * NX) % 2 == 0 && (NX * NU) % 2 == 0) {
+                // identity / zero background in 16-byte stores (the blocks are 16-byte aligned: even strides)
 #pragma unroll
-            for (int r = 0; r < NX; ++r) {
+                for (int e = 0; e < NX * NX; e += 2)
+                    *reinterpret_cast<double2 *>(A + e) = make_double2((e / NX == e % NX) ? 1.0 : 0.0, ((e + 1) / NX == (e + 1) % NX) ? 1.0 : 0.0);
 #pragma unroll
-                for (int k = 0; k < NX; ++k) A[r * NX + k] = (r == k) ? 1.0 : 0.0;
+                for (int e = 0; e < NX * NU; e += 2) *reinterpret_cast<double2 *>(Bm + e) = make_double2(0.0, 0.0);
+            } else {
 #pragma unroll
-                for (int k = 0; k < NU; ++k) Bm[r * NU + k] = 0.0;
+                for (int r = 0; r < NX; ++r) {
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) A[r * NX + k] = (r == k) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < NU; ++k) Bm[r * NU + k] = 0.0;
+                }
             }
             EulerDenseSink sink{A, Bm, NX, NU, bt.dt};
             model_jacobian<M>(x, u, sink);
