@@ -271,7 +271,7 @@ def run_gpu_arm(args):
             "config": {"workload": f"{B} scenarios/GPU x 10-agent Quadcopter12D Potential-iLQR (ilqrSolver.solve), N=50, dt=0.1, "
                                    "n_lqr_iter=50, tol=1e-3, hover warm start, random_setup energy=30 (SURVEY 8d)",
                        "iterations_per_step": iters / args.steps / world,
-                       "l2": "working set per step (K 7.9 GB + candidates 5.3 GB + stage 4.3 GB) >> 126 MB L2",
+                       "l2": "working set per step (K 7.9 GB + candidates 5.3 GB + stage 4.4 GB) >> 126 MB L2",
                        "parallelism": f"scenario-sharded x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x0_pin.numel() * 8 + U0_pin.numel() * 8),
                     "d2h_bytes_per_step": int(sum(b.numel() * b.element_size() for b in out_pin.values())),
