@@ -41,6 +41,8 @@ class BatchStruct(ctypes.Structure):
         ("radius", ctypes.c_void_p),
         ("weights", ctypes.c_void_p),
         ("has_prox", ctypes.c_void_p),
+        ("model_hint", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 

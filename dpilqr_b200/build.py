@@ -15,8 +15,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdpilqr_b200.so")
-SOURCES = ["solver.cu", "forward.cu", "linquad.cu", "backward.cu", "graph.cu", "dynamics_api.cu", "cost_api.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "models.cuh", "cost.cuh", "lu.cuh", os.path.join("..", "..", "include", "dpilqr_b200.h")]
+# (source, object stem, extra flags): the rollout kernel is compiled once per model / size class (rollout_inst.cu)
+ROLLOUT_CLASSES = [0, 1, 2, 3, 4, 5, 6, 7, 8, 100, 101]
+UNITS = [(src, src[:-3], []) for src in ["solver.cu", "forward.cu", "linquad.cu", "backward.cu", "graph.cu", "dynamics_api.cu", "cost_api.cu"]]
+UNITS += [("rollout_inst.cu", f"rollout_c{k}", [f"-DDPILQR_ROLLOUT_CLASS={k}"]) for k in ROLLOUT_CLASSES]
+SOURCES = sorted({u[0] for u in UNITS})
+HEADERS = ["common.cuh", "kernels.cuh", "models.cuh", "cost.cuh", "lu.cuh", "rollout.cuh", os.path.join("..", "..", "include", "dpilqr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++20", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -46,15 +50,16 @@ def build_variant(name, extra_flags):
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
-    def one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        res = subprocess.run([nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+    def one(unit):
+        src, stem, flags = unit
+        obj = os.path.join(objdir, stem + ".o")
+        res = subprocess.run([nvcc, *NVCC_FLAGS, *flags, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(res.stdout + res.stderr)
         return obj
 
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as pool:
-        objs = list(pool.map(one, SOURCES))
+        objs = list(pool.map(one, UNITS))
     out = os.path.join(outdir, name + ".so")
     subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs, "-lcudart"])
     return out
@@ -70,21 +75,22 @@ def build(force=False, verbose=False):
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
 
-    def compile_one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(unit):
+        src, stem, flags = unit
+        obj = os.path.join(objdir, stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log = res.stdout + res.stderr
-        with open(os.path.join(objdir, src + ".log"), "w") as fh:
+        with open(os.path.join(objdir, stem + ".log"), "w") as fh:
             fh.write(log)
         if res.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {src}:\n{log}")
+            raise RuntimeError(f"nvcc failed for {src} {flags}:\n{log}")
         if verbose:
             print(log)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
-        objs = list(pool.map(compile_one, SOURCES))
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, UNITS))
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:

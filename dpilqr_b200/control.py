@@ -9,7 +9,7 @@ kernels.
 import numpy as np
 
 from . import _native
-from .engine import CompiledBatch, spec_from_problem
+from .engine import CompiledBatch, raise_for_status, spec_from_problem
 
 
 class ilqrSolver:
@@ -76,11 +76,7 @@ class ilqrSolver:
         batch = self._compiled()
         stage, st1 = batch.linearize_quadraticize(np.asarray(X)[None], np.asarray(U)[None])
         K, d, st2 = batch.backward(stage, self.μ)
-        status = int(st1.item()) | int(st2.item())
-        if status & _native.ST_POINT_NDIM:
-            raise AssertionError  # reference cost.py:279
-        if status & _native.ST_SINGULAR:
-            raise np.linalg.LinAlgError("Singular matrix")  # what np.linalg.solve raises at control.py:141
+        raise_for_status(int(st1.item()) | int(st2.item()))  # reference cost.py:279, control.py:141
         return K[0].cpu().numpy(), d[0].cpu().numpy()
 
     def solve(self, x0, U=None, n_lqr_iter=50, tol=1e-3, t_kill=None, verbose=True):
@@ -100,10 +96,7 @@ class ilqrSolver:
         out = batch.solve(np.asarray(x0, dtype=np.float64).reshape(1, -1), U[None].astype(np.float64), n_lqr_iter=n_lqr_iter,
                           tol=tol, t_kill=t_kill, trace=True)
         status = int(out["status"][0].item())
-        if status & _native.ST_POINT_NDIM:
-            raise AssertionError
-        if status & _native.ST_SINGULAR:
-            raise np.linalg.LinAlgError("Singular matrix")
+        raise_for_status(status)
         iters = int(out["iters"][0].item())
         acc = out["trace_alpha"][0, :iters].cpu().numpy()
         mus = out["trace_mu"][0, :iters].cpu().numpy()

@@ -27,20 +27,21 @@ __device__ __forceinline__ double numpy_pairwise_block(const double *a, int n)  
     return res;
 }
 
-template <int DEPTH>
-__device__ __forceinline__ double numpy_pairwise_level(const double *a, int n)
+// More than 128 addends (teams of 17 agents and up): NumPy splits the range in halves (the first a multiple of 8)
+// and recurses.  Out of line and truly recursive -- the compile-time unrolled form inlined dozens of copies of the
+// block loop into every kernel that sums pair costs.
+static __device__ __noinline__ double numpy_pairwise_recursive(const double *a, int n)
 {
     if (n <= 128) return numpy_pairwise_block(a, n);
-    if constexpr (DEPTH > 0) {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        return numpy_pairwise_level<DEPTH - 1>(a, n2) + numpy_pairwise_level<DEPTH - 1>(a + n2, n - n2);
-    } else {
-        return __longlong_as_double(0x7ff8000000000000ll);
-    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return numpy_pairwise_recursive(a, n2) + numpy_pairwise_recursive(a + n2, n - n2);
 }
 
-__device__ inline double numpy_pairwise_sum(const double *a, int n) { return numpy_pairwise_level<5>(a, n); }
+__device__ __forceinline__ double numpy_pairwise_sum(const double *a, int n)
+{
+    return n <= 128 ? numpy_pairwise_block(a, n) : numpy_pairwise_recursive(a, n);
+}
 
 // (x - xf) Q (x - xf)^T + u R u^T  (terminal: Qf, no control term) -- reference cost.py:79-83
 template <int M>

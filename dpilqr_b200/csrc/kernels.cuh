@@ -8,6 +8,10 @@ constexpr int kMaxAlpha = 10;
 
 // Trajectories are addressed as  base + b * stride + slot[b] * slot_stride  so the solver loop can
 // keep every problem's current trajectory inside the ping-pong candidate buffers without copies.
+//
+// One launch of the rollout kernel evaluates, for every problem of a list, the `n_alpha` line-search candidates
+// alpha[0..n_alpha-1]; candidate k lands in output slot alpha_first + k (the solver's staged line search launches
+// the kernel up to three times per iteration with different candidate ranges and shrinking lists).
 struct ForwardParams {
     Batch batch;
     const double *X;  // current trajectories (only X[:, 0] is read when K == nullptr)
@@ -21,12 +25,19 @@ struct ForwardParams {
     int64_t xc_stride, uc_stride, jc_stride;  // per-problem strides of the candidate outputs
     int64_t x_slot_stride, u_slot_stride;
     const int32_t *slot;      // may be null
-    const int32_t *active;    // may be null: compacted list of problem indices
+    const int32_t *active;    // may be null: list of problem indices
     const int32_t *n_active;  // may be null: device-side length of `active`
-    int n_alpha;
+    int n_list;               // host-side length of the list (upper bound when n_active is given)
+    int n_alpha;              // candidates per problem in this launch
+    int alpha_first;          // output slot of candidate 0 of this launch
+    int uniform_model;        // model id shared by every agent of the batch, or -1 (mixed team / unknown)
+    int groups_per_cta;       // filled in by the launcher
+    int prefetch;             // filled in by the launcher: L2 prefetch of the next step's gains
     double alpha[kMaxAlpha];
-    long long *timing;  // optional debug cycle counters (slots 24..29 of the dpilqr_debug_backward_timing buffer)
 };
+
+// expected_list: the launcher sizes the groups per CTA for this many problems (the grid always covers n_list)
+int launch_forward(const ForwardParams &p, int expected_list, cudaStream_t stream);
 
 struct LinQuadParams {
     Batch batch;
@@ -60,7 +71,6 @@ struct BackwardParams {
 extern long long *g_backward_timing;
 extern int g_backward_debug_mode;
 
-int launch_forward(const ForwardParams &p, int n_blocks, cudaStream_t stream);
 int launch_linquad(const LinQuadParams &p, int n_problems, cudaStream_t stream);
 int launch_stage_to_dense(const Batch &bt, const double *stage, double *A, double *Bm, double *Lx, double *Lu,
                           double *Lxx, double *Luu, cudaStream_t stream);

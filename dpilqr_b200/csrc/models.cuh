@@ -41,6 +41,13 @@ __host__ __device__ constexpr int model_nu(int m)
          : m == kBike5D ? 2 : -1;
 }
 
+// Pseudo model ids for kernels instantiated per (s, c) size class rather than per model: teams that mix models of
+// one size class (zero-padded heterogeneous teams, reference scripts/examples.py:73-131) dispatch per agent inside.
+constexpr int kMixed4 = 100;  // DoubleInt4D | Unicycle4D
+constexpr int kMixed6 = 101;  // DoubleInt6D | Quad6D | Human6D | HumanLin6D
+__host__ __device__ constexpr int class_nx(int mc) { return mc == kMixed4 ? 4 : mc == kMixed6 ? 6 : model_nx(mc); }
+__host__ __device__ constexpr int class_nu(int mc) { return mc == kMixed4 ? 2 : mc == kMixed6 ? 3 : model_nu(mc); }
+
 constexpr double kGravity = 9.80665;
 // Quadcopter12D rigid-body constants: thrust/mass gain, torque/inertia gains and the
 // gyroscopic coupling ratios (I_j - I_k) / I_i of the airframe the reference models.
@@ -182,21 +189,34 @@ __device__ __forceinline__ void model_step(double dt, double (&x)[model_nx(M)], 
     const double h = (M == kBike5D) ? dt : dt / 5;
     const double hh = h / 2.0;
     const double h6 = h / 6.0;
+    // One rolled loop over the 4 * kSub stage evaluations: the body holds ONE inlined copy of the ODE (the
+    // twenty-fold unrolled form is about 30 kB of SASS for Quadcopter12D and misses the instruction cache).
+    // Stage s of a sub-step:  k = f(xs);  acc += w_s k  (w = 1, 2, 2, 1);  xs = x + c_s k  (c = h/2, h/2, h);
+    // after stage 3:  x += h/6 acc.  Same operations, in the same order, as the textbook form.
+    double acc[NX], xs[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { acc[i] = 0.0; xs[i] = x[i]; }
 #pragma unroll 1
-    for (int sub = 0; sub < kSub; ++sub) {
-        double k[NX], acc[NX], xs[NX];
-        model_f<M>(x, u, k);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i] = k[i]; xs[i] = x[i] + hh * k[i]; }
+    for (int ev = 0; ev < 4 * kSub; ++ev) {
+        const int stage = ev & 3;
+        double k[NX];
         model_f<M>(xs, u, k);
+        const double w = (stage == 0 || stage == 3) ? 1.0 : 2.0;
+        const double cs = (stage == 2) ? h : hh;
+        if (stage == 3) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = x[i] + hh * k[i]; }
-        model_f<M>(xs, u, k);
+            for (int i = 0; i < NX; ++i) {
+                x[i] += h6 * (acc[i] + k[i]);
+                xs[i] = x[i];
+                acc[i] = 0.0;
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i] += 2.0 * k[i]; xs[i] = x[i] + h * k[i]; }
-        model_f<M>(xs, u, k);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] += h6 * (acc[i] + k[i]);
+            for (int i = 0; i < NX; ++i) {
+                acc[i] = fma(w, k[i], acc[i]);
+                xs[i] = fma(cs, k[i], x[i]);
+            }
+        }
     }
 }
 
@@ -335,6 +355,25 @@ __device__ __forceinline__ void dispatch_model(int model, Fn &&fn)
     case kQuad12D: fn.template operator()<kQuad12D>(); break;
     case kBike5D: fn.template operator()<kBike5D>(); break;
     default: break;
+    }
+}
+
+// Dispatch inside a size class: a real model id is a compile-time constant, a mixed class switches per agent.
+template <int MC, class Fn>
+__device__ __forceinline__ void dispatch_class(int model, Fn &&fn)
+{
+    if constexpr (MC == kMixed4) {
+        if (model == kUnicycle4D) fn.template operator()<kUnicycle4D>();
+        else fn.template operator()<kDoubleInt4D>();
+    } else if constexpr (MC == kMixed6) {
+        switch (model) {
+        case kQuad6D: fn.template operator()<kQuad6D>(); break;
+        case kHuman6D: fn.template operator()<kHuman6D>(); break;
+        case kHumanLin6D: fn.template operator()<kHumanLin6D>(); break;
+        default: fn.template operator()<kDoubleInt6D>(); break;
+        }
+    } else {
+        fn.template operator()<MC>();
     }
 }
 

@@ -63,7 +63,7 @@ int validate_batch(const dpilqr_batch *b)
 struct Workspace {
     double *candX[2], *candU[2];
     double *Jc, *K, *d, *stage, *scratch, *mu, *delta, *Jstar, *Jlast;
-    int32_t *slot, *parity, *active[2], *n_active, *flag;
+    int32_t *slot, *parity, *active[2], *n_active, *flag, *ls_list[2], *ls_count;
     int64_t bytes;
 };
 
@@ -97,8 +97,11 @@ static Workspace carve(char *base, int B, int a, int s, int c, int T, int NA)
     w.parity = (int32_t *)take((int64_t)B * 4);
     w.active[0] = (int32_t *)take((int64_t)B * 4);
     w.active[1] = (int32_t *)take((int64_t)B * 4);
+    w.ls_list[0] = (int32_t *)take((int64_t)B * 4);
+    w.ls_list[1] = (int32_t *)take((int64_t)B * 4);
     w.n_active = (int32_t *)take(256);
     w.flag = (int32_t *)take(256);
+    w.ls_count = (int32_t *)take(256);
     w.bytes = off;
     return w;
 }
@@ -206,6 +209,51 @@ __global__ void __launch_bounds__(1024) select_kernel(int iter, int n_iter, int 
     if (tid == 0) *n_active = chunk_base;
 }
 
+// Staged line search (the reference tries the candidates one after the other and stops at the first improvement,
+// control.py:179-193; 64 % of the iterations of the metric batch accept the first one): after the candidates
+// [k0, k1) have been rolled out for the problems of `list_in`, the problems none of them improved move on to
+// `list_out` (ordered compaction); for the others the costs of the candidates never tried are marked NaN.
+__global__ void __launch_bounds__(1024) stage_select_kernel(int k0, int k1, int NA, const double *Jstar, double *Jc,
+                                                            const int32_t *list_in, const int32_t *count_in,
+                                                            int32_t *list_out, int32_t *count_out)
+{
+    __shared__ int warp_counts[32];
+    __shared__ int chunk_base;
+    const int count = *count_in;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) chunk_base = 0;
+    __syncthreads();
+    for (int base = 0; base < count; base += blockDim.x) {
+        const int idx = base + tid;
+        bool keep = false;
+        int b = -1;
+        if (idx < count) {
+            b = list_in[idx];
+            double *J = Jc + (int64_t)b * NA;
+            const double Js = Jstar[b];
+            bool improved = false;
+            for (int k = k0; k < k1; ++k) improved = improved || (J[k] < Js);
+            keep = !improved;
+            if (improved)
+                for (int k = k1; k < NA; ++k) J[k] = __longlong_as_double(0x7ff8000000000000ll);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_counts[warp] = __popc(ballot);
+        __syncthreads();
+        int prefix = 0, total = 0;
+        const int nwarps = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nwarps; ++w) {
+            if (w < warp) prefix += warp_counts[w];
+            total += warp_counts[w];
+        }
+        if (keep) list_out[chunk_base + prefix + __popc(ballot & ((1u << lane) - 1))] = b;
+        __syncthreads();
+        if (tid == 0) chunk_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) *count_out = chunk_base;
+}
+
 __global__ void mark_time_limit_kernel(const int32_t *active, const int32_t *n_active, int32_t *status)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,6 +358,8 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
     fp.xc_stride = NA * xlen; fp.uc_stride = NA * ulen; fp.jc_stride = NA;
     fp.n_alpha = 1;
     fp.alpha[0] = 0.0;
+    fp.n_list = B;
+    fp.uniform_model = batch->model_hint - 1;
     LaunchTimer timer(opts->profile != 0, stream);
     timer.begin(DPILQR_K_ROLLOUT, B);
     rc = launch_forward(fp, B, stream);
@@ -351,18 +401,42 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
         timer.end();
         if (rc) break;
 
+        // staged line search: candidate 0 for every active problem, candidates 1..2 for those it did not improve,
+        // the rest for those still without an improvement (lists and counts stay on the device; the grids are
+        // sized for the host-side bound n_act and surplus CTAs leave at once)
         ForwardParams ls{};
         ls.batch = *batch;
         ls.X = w.candX[cur]; ls.U = w.candU[cur];
         ls.x_stride = NA * xlen; ls.u_stride = NA * ulen; ls.x_slot_stride = xlen; ls.u_slot_stride = ulen;
-        ls.slot = w.slot; ls.active = act; ls.n_active = w.n_active;
+        ls.slot = w.slot;
         ls.K = w.K; ls.d = w.d;
         ls.Xc = w.candX[nxt]; ls.Uc = w.candU[nxt]; ls.Jc = w.Jc;
         ls.xc_stride = NA * xlen; ls.uc_stride = NA * ulen; ls.jc_stride = NA;
-        ls.n_alpha = NA;
-        for (int k = 0; k < NA; ++k) ls.alpha[k] = kAlphaTable[k];
+        ls.n_list = n_act;
+        ls.uniform_model = batch->model_hint - 1;
+        const int bounds[4] = {0, NA < 1 ? NA : 1, NA < 3 ? NA : 3, NA};
+        const double expect[3] = {1.0, 0.45, 0.3};  // share of the active problems that reaches each stage (metric batch)
+        const int32_t *list_in = act;
+        const int32_t *count_in = w.n_active;
         timer.begin(DPILQR_K_LINESEARCH, n_act);
-        rc = launch_forward(ls, n_act, stream);
+        for (int stg = 0; stg < 3 && !rc; ++stg) {
+            const int k0 = bounds[stg], k1 = bounds[stg + 1];
+            if (k1 <= k0) continue;
+            ls.active = list_in; ls.n_active = count_in;
+            ls.alpha_first = k0; ls.n_alpha = k1 - k0;
+            for (int k = k0; k < k1; ++k) ls.alpha[k - k0] = kAlphaTable[k];
+            int expected = (int)(expect[stg] * n_act) + 1;
+            rc = launch_forward(ls, expected, stream);
+            if (rc) break;
+            if (k1 < NA) {
+                int32_t *list_out = w.ls_list[stg & 1];
+                int32_t *count_out = w.ls_count + stg;
+                stage_select_kernel<<<1, 1024, 0, stream>>>(k0, k1, NA, w.Jstar, w.Jc, list_in, count_in, list_out, count_out);
+                rc = check_cuda(cudaGetLastError(), "stage_select_kernel");
+                list_in = list_out;
+                count_in = count_out;
+            }
+        }
         timer.end();
         if (rc) break;
 
@@ -410,7 +484,7 @@ using namespace dpilqr;
 extern "C" {
 
 const char *dpilqr_last_error(void) { return g_error; }
-int dpilqr_version(void) { return 100; }
+int dpilqr_version(void) { return 200; }
 
 int dpilqr_device_count(void)
 {
@@ -467,9 +541,19 @@ int dpilqr_rollout_linesearch(const dpilqr_batch *batch, const double *X, const 
     fp.u_stride = T * m;
     fp.Xc = Xc; fp.Uc = Uc; fp.Jc = Jc;
     fp.xc_stride = (int64_t)n_alpha * (T + 1) * n; fp.uc_stride = (int64_t)n_alpha * T * m; fp.jc_stride = n_alpha;
-    fp.n_alpha = n_alpha;
-    for (int k = 0; k < n_alpha; ++k) fp.alpha[k] = alphas ? alphas[k] : kAlphaTable[k];
-    return launch_forward(fp, batch->n_problems, (cudaStream_t)stream);
+    fp.n_list = batch->n_problems;
+    fp.uniform_model = batch->model_hint - 1;
+    // the kernel takes up to kRolloutMaxThreads / a candidates of a problem per launch: wide teams go in chunks
+    int chunk = n_alpha;
+    while (chunk > 1 && chunk * batch->n_agents > 256) --chunk;
+    for (int k0 = 0; k0 < n_alpha; k0 += chunk) {
+        fp.alpha_first = k0;
+        fp.n_alpha = (n_alpha - k0 < chunk) ? n_alpha - k0 : chunk;
+        for (int k = 0; k < fp.n_alpha; ++k) fp.alpha[k] = alphas ? alphas[k0 + k] : kAlphaTable[k0 + k];
+        rc = launch_forward(fp, batch->n_problems, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return DPILQR_OK;
 }
 
 int dpilqr_linearize_quadraticize(const dpilqr_batch *batch, const double *X, const double *U, double *stage,

@@ -151,7 +151,9 @@ class CompiledBatch:
                 last = (Q, R, Qf, idx)
         dev = self.device
         f64 = dict(dtype=torch.float64, device=dev)
-        self.t_model = torch.as_tensor(np.array([sp.models for sp in specs], dtype=np.int32)).to(dev)
+        models_np = np.array([sp.models for sp in specs], dtype=np.int32)
+        self.model_hint = int(models_np.flat[0]) + 1 if np.all(models_np == models_np.flat[0]) else 0
+        self.t_model = torch.as_tensor(models_np).to(dev)
         self.t_ndims = torch.as_tensor(np.array([sp.n_dims for sp in specs], dtype=np.int32)).to(dev)
         self.t_cidx = torch.as_tensor(cost_idx).to(dev)
         self.t_Q = torch.as_tensor(np.stack(Qs)).to(**f64).contiguous()
@@ -169,7 +171,7 @@ class CompiledBatch:
             self.B, self.a, self.s, self.c, int(horizon), int(self.t_Q.shape[0]), self.dt,
             self.t_model.data_ptr(), self.t_ndims.data_ptr(), self.t_cidx.data_ptr(), self.t_Q.data_ptr(),
             self.t_R.data_ptr(), self.t_Qf.data_ptr(), self.t_xf.data_ptr(), self.t_radius.data_ptr(),
-            self.t_weights.data_ptr(), self.t_hasprox.data_ptr(),
+            self.t_weights.data_ptr(), self.t_hasprox.data_ptr(), self.model_hint, 0,
         )
 
     # ---------------------------------------------------------------- helpers
@@ -305,10 +307,27 @@ def bin_specs(specs):
     return bins
 
 
-def solve_specs(specs, x0s, U0s, N, device=None, **kw):
+def raise_for_status(status):
+    """The exceptions the reference raises for one problem, from its status word: the ``Point.ndim`` assertion of
+    quadraticize_distance (reference cost.py:279) and np.linalg.solve's LinAlgError for a singular Q_uu
+    (reference control.py:141-142)."""
+    status = int(status)
+    if status & _native.ST_POINT_NDIM:
+        raise AssertionError
+    if status & _native.ST_SINGULAR:
+        raise np.linalg.LinAlgError("Singular matrix")
+
+
+def solve_specs(specs, x0s, U0s, N, device=None, on_error="raise", **kw):
     """Solve a ragged list of problems: bin, solve each bin in one batch, scatter back.
 
-    Returns a list of per-problem dicts of NumPy arrays (X, U, J, J_star, iters, status[, trace_*])."""
+    Returns a list of per-problem dicts of NumPy arrays (X, U, J, J_star, iters, status[, trace_*]).
+    ``on_error="raise"`` (default): the first problem, in list order, whose solve the reference would have aborted
+    with an exception raises that exception here too (every sub-problem of the reference goes through
+    ilqrSolver.solve, so solve_distributed / solve_rhc / selfish_warmstart abort the same way);
+    ``on_error="status"`` leaves the decision to the caller (per-problem ``status`` words)."""
+    if on_error not in ("raise", "status"):
+        raise ValueError("on_error must be 'raise' or 'status'")
     results = [None] * len(specs)
     for key, idxs in bin_specs(specs).items():
         batch = CompiledBatch([specs[k] for k in idxs], N, device)
@@ -318,4 +337,7 @@ def solve_specs(specs, x0s, U0s, N, device=None, **kw):
         host = {k: v.cpu().numpy() for k, v in out.items() if isinstance(v, torch.Tensor)}
         for j, k in enumerate(idxs):
             results[k] = {name: arr[j] for name, arr in host.items()}
+    if on_error == "raise":
+        for res in results:
+            raise_for_status(res["status"])
     return results

@@ -86,6 +86,9 @@ typedef struct dpilqr_batch {
     const double *radius;    /* [B]     ProximityCost.radius; ignored when a == 1 */
     const double *weights;   /* [B][2]  GameCost.REF_WEIGHT, GameCost.PROX_WEIGHT (cost.py:185-186) */
     const int32_t *has_prox; /* [B] 0: no proximity term (bare ReferenceCost or GameCost(.., None)) */
+    int32_t model_hint;      /* 1 + DPILQR_MODEL_* when EVERY agent of EVERY problem runs that model (selects the rollout
+                                kernel compiled for it alone); 0 (a zeroed struct): per-agent dispatch in the size class */
+    int32_t reserved;        /* 0 */
 } dpilqr_batch;
 
 /* ---- solver options: arguments of ilqrSolver.solve (reference control.py:150) ---- */

@@ -395,6 +395,7 @@ class OracleSolver:
         self.delta = self.DELTA_0
         self.trace = []  # one dict per outer iteration
         self.n_backward = 0
+        self.cond_log = None  # set to a list to record cond(Q_uu) of every step of every backward pass
 
     def rollout(self, x0, U):
         """_rollout (control.py:80-93)."""
@@ -440,6 +441,8 @@ class OracleSolver:
             Q_xx = L_xx + A.T @ P @ A
             Q_uu = L_uu + B.T @ (P + reg) @ B
             Q_ux = L_ux + B.T @ (P + reg) @ A
+            if self.cond_log is not None:
+                self.cond_log.append(np.linalg.cond(Q_uu))
             K[t] = -np.linalg.solve(Q_uu, Q_ux)
             d[t] = -np.linalg.solve(Q_uu, Q_u)
             p = Q_x + K[t].T @ Q_uu @ d[t] + K[t].T @ Q_u + Q_ux.T @ d[t]

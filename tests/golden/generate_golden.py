@@ -344,8 +344,186 @@ def gen_solves():
         run_centralized(f"misc_{model}_a3", c)
 
 
+# --------------------------------------------------------------------------- #
+# receding horizon (distributed.py:106-221), selfish warm start (problem.py:66-91),
+# RecedingHorizonController (control.py:253-326)
+# --------------------------------------------------------------------------- #
+class _FixedWarmStart:
+    """Stands in for ``np.random.rand(N, n_u)`` inside the reference's solve_rhc (distributed.py:152): the product
+    ``* 0.01`` returns the wanted warm start, so the UNMODIFIED reference runs from e.g. hover controls."""
+
+    def __init__(self, U):
+        self.U = U
+
+    def __mul__(self, _):
+        return self.U.copy()
+
+
+class RoundRecorder:
+    """Wraps the reference's solve_distributed / solve_centralized (looked up as module globals by solve_rhc) and
+    records every round's inputs and outputs."""
+
+    def __init__(self):
+        self.rounds = []
+
+    def __enter__(self):
+        mod = sys.modules[ref.solve_rhc.__module__]
+        self.mod, self._sd, self._sc = mod, mod.solve_distributed, mod.solve_centralized
+        rec = self
+
+        def sd(problem, X, U, *args, **kw):
+            out = rec._sd(problem, X, U, *args, **kw)
+            rec.rounds.append(dict(X_in=np.array(X), U_in=np.array(U), X=out[0].copy(), U=out[1].copy(), J=out[2],
+                                   graph={k: list(v[1]) for k, v in out[3].items()}))
+            return out
+
+        def sc(solver, xi, U, ids, verbose, **kw):
+            out = rec._sc(solver, xi, U, ids, verbose, **kw)
+            rec.rounds.append(dict(X_in=np.array(xi).reshape(1, -1), U_in=np.array(U), X=out[0].copy(), U=out[1].copy(), J=out[2],
+                                   graph={}))
+            return out
+
+        mod.solve_distributed, mod.solve_centralized = sd, sc
+        return self
+
+    def __exit__(self, *exc):
+        self.mod.solve_distributed, self.mod.solve_centralized = self._sd, self._sc
+
+
+def run_rhc(name, case, N, radius_graph, centralized, rhc_kw, U_init=None, seed=None, solver_kw=None):
+    """One full solve_rhc of the unmodified reference + the same run from x0 * (1 +- 1e-15) (sensitivity)."""
+    solver_kw = solver_kw or {}
+    ids = list(case["ids"])
+
+    def once(x0):
+        ref._reset_ids()
+        prob = build_problem(list(case["models"]), case["dt"], case["xf"], case["Q"], case["R"], case["Qf"],
+                             case["radius"], case["n_dims"], ids)
+        if seed is not None:
+            np.random.seed(seed)
+        saved = np.random.rand
+        if U_init is not None:
+            np.random.rand = lambda *shape: _FixedWarmStart(U_init)
+        try:
+            with RoundRecorder() as rr:
+                args = () if centralized else (radius_graph, [])
+                X, U, J = ref.solve_rhc(prob, x0.reshape(-1, 1), N, *args, centralized=centralized, **rhc_kw, **solver_kw)
+        finally:
+            np.random.rand = saved
+        return X, U, J, rr.rounds, prob
+
+    X, U, J, rounds, prob = once(case["x0"])
+    signs = np.sign(np.random.default_rng(2024).normal(size=case["x0"].shape))
+    X2, U2, J2, rounds2, _ = once(case["x0"] * (1 + 1e-15 * signs))
+    same = X.shape == X2.shape
+    sens_X = float(np.max(np.abs(X - X2)) / np.max(np.abs(X))) if same else np.inf
+    sens_U = float(np.max(np.abs(U - U2)) / np.max(np.abs(U))) if same else np.inf
+    R = len(rounds)
+    a = len(ids)
+    adj = np.zeros((R, a, a), dtype=np.int8)
+    rows_in = np.array([r["X_in"].shape[0] for r in rounds])
+    Xin = np.zeros((R, N + 1, X.shape[1]))
+    round_sens = np.full(R, np.inf)
+    for k, r in enumerate(rounds):
+        Xin[k, : rows_in[k]] = r["X_in"]
+        for i, id_ in enumerate(ids):
+            for other in r["graph"].get(id_, []):
+                adj[k, i, ids.index(int(other))] = 1
+        if k < len(rounds2) and rounds2[k]["X"].shape == r["X"].shape:
+            round_sens[k] = max(np.max(np.abs(r["X"] - rounds2[k]["X"])) / np.max(np.abs(r["X"])),
+                                np.max(np.abs(r["U"] - rounds2[k]["U"])) / max(np.max(np.abs(r["U"])), 1e-300))
+    # teacher-forced sensitivity of every round: the reference's own round solve from the SAME recorded input,
+    # perturbed by 1e-15 relative (first row of X_in: only X_in[0] enters the sub-problem solves)
+    round_sens_tf = np.full(R, np.inf)
+    for k, r in enumerate(rounds):
+        sg = np.sign(np.random.default_rng(7 + k).normal(size=r["X_in"].shape))
+        Xp = r["X_in"] * (1 + 1e-15 * sg)
+        if centralized:
+            ref._reset_ids()
+            Xk, Uk, _ = ref.ilqrSolver(prob, N).solve(Xp.reshape(-1, 1), r["U_in"].copy(), verbose=False, **solver_kw)
+        else:
+            Xk, Uk, _, _ = ref.solve_distributed(prob, Xp, r["U_in"].copy(), radius_graph, [], None, False, **solver_kw)
+        round_sens_tf[k] = max(np.max(np.abs(r["X"] - Xk)) / np.max(np.abs(r["X"])),
+                               np.max(np.abs(r["U"] - Uk)) / max(np.max(np.abs(r["U"])), 1e-300))
+    out = dict(case)
+    out.pop("U0", None)
+    out.update(round_sens_tf=round_sens_tf)
+    out.update(N=N, radius_graph=radius_graph if radius_graph is not None else 0.0, centralized=centralized,
+               n_d=rhc_kw.get("n_d", 2), step_size=rhc_kw.get("step_size", 1),
+               dist_converge=rhc_kw.get("dist_converge") or 0.0, J_converge=rhc_kw.get("J_converge") or 0.0,
+               t_diverge=rhc_kw.get("t_diverge") or 0.0, seed=-1 if seed is None else seed,
+               has_U_init=U_init is not None, U_init=U_init if U_init is not None else rounds[0]["U_in"],
+               n_lqr_iter=solver_kw.get("n_lqr_iter", 50), tol=solver_kw.get("tol", 1e-3),
+               X_full=X, U_full=U, J_full=J, sens_X=sens_X, sens_U=sens_U, sens_J=abs(J - J2) / abs(J),
+               round_rows_in=rows_in, round_X_in=Xin, round_U_in=np.stack([r["U_in"] for r in rounds]),
+               round_X=np.stack([r["X"] for r in rounds]), round_U=np.stack([r["U"] for r in rounds]),
+               round_J=np.array([r["J"] for r in rounds]), round_adjacency=adj, round_sens=round_sens)
+    np.savez_compressed(os.path.join(OUT, f"rhc_{name}.npz"), **out)
+    print(f"rhc_{name}: rounds={R} X_full{X.shape} J_full={J:.6g} sens_X={sens_X:.1e} round_sens_max={round_sens.max():.1e} "
+          f"teacher-forced round sens={np.array2string(round_sens_tf, precision=1)}")
+
+
+def gen_rhc():
+    I = np.eye
+    # config 1 family: 3 x DoubleInt4D, centralized and decentralised receding horizon (well conditioned)
+    c1 = random_case("DoubleInt4D", 3, 0, 10.0, 2, np.diag([1.0, 1, 0, 0]), I(2), 1000 * I(4))
+    kw = dict(n_d=2, step_size=3, dist_converge=0.3, t_diverge=6 * 0.1)
+    run_rhc("cfg1_dint4_a3_central", c1, 20, None, True, kw, seed=11)
+    run_rhc("cfg1_dint4_a3_dec", c1, 20, 0.5, False, kw, seed=11)
+    # (J_converge mode cannot be pinned: the unmodified reference raises NameError at distributed.py:131/189 there,
+    # because n_agents / n_states are only bound in the dist_converge branch :141-142)
+    # config 3 as configured (scripts/examples.py:86-130, scenarios.py:145-152): 2 x Quad6D + Human6D, decentralised,
+    # n_d=3, step_size=3, dist_converge=0.1, the reference's own 0.01*rand warm start
+    x0 = np.array([-1.5, 0.1, 1, 0, 0, 0, 1.5, 0, 1, 0, 0, 0, 0, -1, 1.5, 0, 0, 0.0])
+    xf = np.array([1.5, 0, 2, 0, 0, 0, -1.5, 0, 2, 0, 0, 0, 0.0, 2, 1.5, 0, 0, 0])
+    Qq, Rq, Qfq = np.diag([1.0, 1, 1, 5, 5, 5]), np.diag([1.0, 1, 1]), 1e3 * I(6)
+    Qh, Rh = np.diag([1.0, 1, 1, 0, 0, 0]), np.diag([1, 1, 1e-9])
+    c3 = case_dict(["Quadcopter6D", "Quadcopter6D", "Human6D"], 0.05, 50, x0, xf, [Qq, Qq, Qh], [Rq, Rq, Rh],
+                   [Qfq, Qfq, Qfq], 0.3, [3, 3, 2], [100, 101, 102], np.zeros((50, 9)), 50, 1e-3)
+    run_rhc("cfg3_q6q6h6_dec", c3, 50, 0.3, False, dict(n_d=3, step_size=3, dist_converge=0.1, t_diverge=50 * 0.05), seed=0)
+    # config 4: 15 x Quad12D decentralised receding horizon with dynamic interaction graphs, hover warm start, 4 rounds
+    c4 = random_case("Quadcopter12D", 15, 0, 45.0, 3, I(12), I(4), 1000 * I(12), U0=hover(50, 15))
+    run_rhc("cfg4_quad12_a15_dec", c4, 50, 0.5, False, dict(n_d=3, step_size=5, dist_converge=0.1, t_diverge=3 * 5 * 0.1),
+            U_init=hover(50, 15), solver_kw=dict(n_lqr_iter=8))
+
+
+def gen_warmstart():
+    """ilqrProblem.selfish_warmstart (problem.py:66-91) and RecedingHorizonController (control.py:253-326)."""
+    import contextlib
+    import io
+
+    I = np.eye
+    out = {}
+    for tag, case in [("dint4", random_case("DoubleInt4D", 3, 0, 10.0, 2, np.diag([1.0, 1, 0, 0]), I(2), 1000 * I(4))),
+                      ("uni4", random_case("Unicycle4D", 5, 1, 10.0, 2, np.diag([1.0, 1, 0, 0]), I(2), 1000 * I(4)))]:
+        ref._reset_ids()
+        prob = build_problem(list(case["models"]), case["dt"], case["xf"], case["Q"], case["R"], case["Qf"],
+                             case["radius"], case["n_dims"], list(case["ids"]))
+        with contextlib.redirect_stdout(io.StringIO()):
+            U_warm = prob.selfish_warmstart(case["x0"].reshape(-1, 1), int(case["N"]))
+        for k, v in case.items():
+            out[f"{tag}_{k}"] = v
+        out[f"{tag}_U_warm"] = U_warm
+    # RecedingHorizonController on the 3 x DoubleInt4D problem
+    case = random_case("DoubleInt4D", 3, 0, 10.0, 2, np.diag([1.0, 1, 0, 0]), I(2), 1000 * I(4))
+    ref._reset_ids()
+    prob = build_problem(list(case["models"]), case["dt"], case["xf"], case["Q"], case["R"], case["Qf"],
+                         case["radius"], case["n_dims"], list(case["ids"]))
+    N, step = 15, 2
+    ctrl = ref.RecedingHorizonController(case["x0"].reshape(-1, 1), ref.ilqrSolver(prob, N), step_size=step)
+    Xs, Us, Js = [], [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for k, (Xk, Uk, Jk) in enumerate(ctrl.solve(np.zeros((N, 6)), J_converge=250.0, verbose=False)):
+            Xs.append(Xk), Us.append(Uk), Js.append(Jk)
+            if k >= 7:
+                break
+    out.update(rhc_N=N, rhc_step=step, rhc_J_converge=250.0, rhc_X=np.stack(Xs), rhc_U=np.stack(Us), rhc_J=np.array(Js))
+    np.savez_compressed(os.path.join(OUT, "warmstart.npz"), **out)
+    print(f"warmstart.npz written (RecedingHorizonController horizons={len(Js)}, J={Js})")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dynamics", "cost", "graphs", "solves"]
+    which = sys.argv[1:] or ["dynamics", "cost", "graphs", "solves", "rhc", "warmstart"]
     if "dynamics" in which:
         gen_dynamics()
     if "cost" in which:
@@ -354,3 +532,7 @@ if __name__ == "__main__":
         gen_graphs()
     if "solves" in which:
         gen_solves()
+    if "rhc" in which:
+        gen_rhc()
+    if "warmstart" in which:
+        gen_warmstart()

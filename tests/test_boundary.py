@@ -50,7 +50,7 @@ def test_struct_layout_matches_header(built_lib):
 
     from dpilqr_b200 import _native
 
-    assert ctypes.sizeof(_native.BatchStruct) == 6 * 4 + 8 + 10 * 8
+    assert ctypes.sizeof(_native.BatchStruct) == 6 * 4 + 8 + 10 * 8 + 2 * 4
     assert ctypes.sizeof(_native.SolveOpts) == 32
 
 
