@@ -56,6 +56,8 @@ class SolveOpts(ctypes.Structure):
         ("t_kill", ctypes.c_double),
         ("record_trace", ctypes.c_int32),
         ("profile", ctypes.c_int32),
+        ("bounded_search", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -76,6 +78,7 @@ ST_CONVERGED = 16
 ST_LS_FAILED = 32
 ST_ITER_LIMIT = 64
 ST_TIME_LIMIT = 128
+J_ABORTED = 1.7976931348623157e308  # DPILQR_J_ABORTED: candidate stopped by the bounded line search
 
 EXPORTS = [
     "dpilqr_last_error", "dpilqr_version", "dpilqr_device_count", "dpilqr_model_nx", "dpilqr_model_nu",

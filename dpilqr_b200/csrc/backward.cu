@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             if (x2 > k) Lp[k * LDF + x2] = v;   // l(x2, k)
             else Up[k * LDF + x2] = v;          // u(x2, k): column k, row x2 <= k
             if (x2 == k) {
-                if (!(fabs(v) > 0.0)) st |= DPILQR_ST_SINGULAR;  // exact zero (or NaN) pivot
+                if (v == 0.0) st |= DPILQR_ST_SINGULAR;  // exact zero pivot: dgesv's info > 0 (a NaN pivot is not: np.linalg.solve returns NaN)
                 rdiag[k] = __drcp_rn(v);
             }
         }

@@ -5,8 +5,10 @@
 
 namespace dpilqr {
 
-int launch_forward(const ForwardParams &p, int expected_list, cudaStream_t stream)
+int launch_forward(const ForwardParams &p_in, int expected_list, cudaStream_t stream)
 {
+    ForwardParams p = p_in;
+    p.timing = g_backward_timing;
     const Batch &bt = p.batch;
     if (p.n_alpha < 1 || p.n_alpha > kMaxAlpha) {
         set_error("n_alpha must be in 1..%d (got %d)", kMaxAlpha, p.n_alpha);
@@ -31,6 +33,10 @@ int launch_forward(const ForwardParams &p, int expected_list, cudaStream_t strea
     else if (bt.s == 6 && bt.c == 3)
         mc = (p.uniform_model == kDoubleInt6D || p.uniform_model == kQuad6D || p.uniform_model == kHuman6D || p.uniform_model == kHumanLin6D)
                  ? p.uniform_model : kMixed6;
+    if (mc < 0) {
+        set_error("rollout kernel: unsupported per-agent dimensions (%d, %d)", bt.s, bt.c);
+        return DPILQR_E_UNSUPPORTED;
+    }
     switch (mc) {
     case kDoubleInt4D: return launch_rollout_class<kDoubleInt4D>(p, expected_list, stream);
     case kDoubleInt6D: return launch_rollout_class<kDoubleInt6D>(p, expected_list, stream);
@@ -45,7 +51,6 @@ int launch_forward(const ForwardParams &p, int expected_list, cudaStream_t strea
     case kMixed6: return launch_rollout_class<kMixed6>(p, expected_list, stream);
     default: break;
     }
-    set_error("rollout kernel: unsupported per-agent dimensions (%d, %d)", bt.s, bt.c);
     return DPILQR_E_UNSUPPORTED;
 }
 

@@ -33,7 +33,13 @@ struct ForwardParams {
     int uniform_model;        // model id shared by every agent of the batch, or -1 (mixed team / unknown)
     int groups_per_cta;       // filled in by the launcher
     int prefetch;             // filled in by the launcher: L2 prefetch of the next step's gains
+    int chunk_alpha;          // filled in by the launcher: candidates per group (the launch's candidates in equal chunks)
+    int n_chunks;             // filled in by the launcher
+    int stage_gains;          // filled in by the launcher: K[t] of the CTA's groups staged in shared memory by TMA, a step ahead
+    const double *J_bound;    // may be null: per-problem cost bound of the bounded line search (the solver's J*)
+    int exempt_cand;          // output slot never stopped by the bound (the solver's last candidate), or -1
     double alpha[kMaxAlpha];
+    long long *timing;        // optional debug cycle counters of CTA 0 / thread 0 (slots 24..31 of the dpilqr_debug_backward_timing buffer)
 };
 
 // expected_list: the launcher sizes the groups per CTA for this many problems (the grid always covers n_list)

@@ -68,28 +68,50 @@ constexpr double kGyroZ = 9976479919918.0 / 271597947137541.0;
 // ------------------------------------------------------------------------------------------
 static __device__ __noinline__ void ode_sincos_library(double x, double *sn, double *cs) { sincos(x, sn, cs); }
 
+// Polynomial and reduction constants live in constant memory: as immediates every one of them costs two UMOV
+// instructions per use inside the rolled integrator loop (a fifth of all issued instructions, measured), as
+// constant-bank operands they ride along in the DFMA for free.
+static __constant__ double kSinCosC[16] = {
+    6.36619772367581382433e-01,   // 0  2/pi
+    1.5707963267948966,           // 1  pi/2 high
+    6.123233995736766e-17,        // 2  pi/2 low
+    1.58969099521155010221e-10,   // 3  sin
+    -2.50507602534068634195e-08,  // 4
+    2.75573137070700676789e-06,   // 5
+    -1.98412698298579493134e-04,  // 6
+    8.33333333332248946124e-03,   // 7
+    -1.66666666666666324348e-01,  // 8
+    -1.13596475577881948265e-11,  // 9  cos
+    2.08757232129817482790e-09,   // 10
+    -2.75573143513906633035e-07,  // 11
+    2.48015872894767294178e-05,   // 12
+    -1.38888888888741095749e-03,  // 13
+    4.16666666666666019037e-02,   // 14
+    0.0};
+
 __device__ __forceinline__ void ode_sincos(double x, double *sn, double *cs)
 {
     if (!(fabs(x) < 1.0e5)) {  // rare; out of line so the hot path stays compact
         ode_sincos_library(x, sn, cs);
         return;
     }
-    const double kd = rint(x * 6.36619772367581382433e-01);
+    const double *K = kSinCosC;
+    const double kd = rint(x * K[0]);
     const int k = __double2int_rn(kd);
-    double r = fma(-kd, 1.5707963267948966, x);
-    r = fma(-kd, 6.123233995736766e-17, r);
+    double r = fma(-kd, K[1], x);
+    r = fma(-kd, K[2], r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, K[3], K[4]);
+    ps = fma(z, ps, K[5]);
+    ps = fma(z, ps, K[6]);
+    ps = fma(z, ps, K[7]);
+    ps = fma(z, ps, K[8]);
     const double s = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, K[9], K[10]);
+    pc = fma(z, pc, K[11]);
+    pc = fma(z, pc, K[12]);
+    pc = fma(z, pc, K[13]);
+    pc = fma(z, pc, K[14]);
     const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
     double ss = (k & 1) ? c : s;
     double cc = (k & 1) ? s : c;
@@ -97,6 +119,43 @@ __device__ __forceinline__ void ode_sincos(double x, double *sn, double *cs)
     if ((k + 1) & 2) cc = -cc;
     *sn = ss;
     *cs = cc;
+}
+
+// Three angles at once, as one straight-line block: the compiler interleaves the three dependency chains (evaluated
+// one after the other -- each behind its own range-check branch -- they cost three times the latency).
+__device__ __forceinline__ void ode_sincos3(const double (&x)[3], double (&sn)[3], double (&cs)[3])
+{
+    if (!(fabs(x[0]) < 1.0e5 && fabs(x[1]) < 1.0e5 && fabs(x[2]) < 1.0e5)) {
+        for (int i = 0; i < 3; ++i) ode_sincos_library(x[i], &sn[i], &cs[i]);
+        return;
+    }
+    const double *K = kSinCosC;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double kd = rint(x[i] * K[0]);
+        const int k = __double2int_rn(kd);
+        double r = fma(-kd, K[1], x[i]);
+        r = fma(-kd, K[2], r);
+        const double z = r * r;
+        double ps = fma(z, K[3], K[4]);
+        ps = fma(z, ps, K[5]);
+        ps = fma(z, ps, K[6]);
+        ps = fma(z, ps, K[7]);
+        ps = fma(z, ps, K[8]);
+        const double s = fma(r * z, ps, r);
+        double pc = fma(z, K[9], K[10]);
+        pc = fma(z, pc, K[11]);
+        pc = fma(z, pc, K[12]);
+        pc = fma(z, pc, K[13]);
+        pc = fma(z, pc, K[14]);
+        const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+        double ss = (k & 1) ? c : s;
+        double cc = (k & 1) ? s : c;
+        if (k & 2) ss = -ss;
+        if ((k + 1) & 2) cc = -cc;
+        sn[i] = ss;
+        cs[i] = cc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -215,6 +274,104 @@ __device__ __forceinline__ void model_step(double dt, double (&x)[model_nx(M)], 
             for (int i = 0; i < NX; ++i) {
                 acc[i] = fma(w, k[i], acc[i]);
                 xs[i] = fma(cs, k[i], x[i]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Quadcopter12D integrated by a TEAM of three warps (the rollout kernel): lane q of every warp of the team works on
+// agent q of the team's 32 agents, and the warp's ROLE owns a slice of the state and of the RK4 arithmetic --
+//   role 0: Euler angles (x3..5): the three sin/cos pairs and the angle rates -- the serial spine of the ODE
+//           (angles -> sincos -> rates -> angles);
+//   role 1: position p (x0..2) = R(angles) v;
+//   role 2: body velocity and rates v, w (x6..11).
+// Per ODE evaluation role 2 publishes v, w and role 0 the six trig values of the stage state in a double-buffered
+// shared-memory scratch [2][12][32] (component-major: conflict-free), then ONE named barrier of 96 threads, then
+// every role evaluates its slice.  Same expressions as model_f_inline<kQuad12D> / model_step; a warp only ever runs
+// its own role's code (no divergence), so an evaluation costs the spine instead of the whole ODE -- the rollout is
+// bound by the latency of 20 dependent ODE evaluations per step, and a batch of 4096 ten-drone problems is only
+// 41 k agents, a seventh of the threads the GPU holds.
+// ------------------------------------------------------------------------------------------
+constexpr int kTeamRoles = 3;
+constexpr int kTeamThreads = 32 * kTeamRoles;
+constexpr int kTeamScratch = 2 * 12 * 32;  // doubles per team
+__host__ __device__ constexpr int team_role_offset(int role) { return role == 0 ? 3 : role == 1 ? 0 : 6; }  // first state component
+__host__ __device__ constexpr int team_role_count(int role) { return role == 2 ? 6 : 3; }
+
+__device__ __forceinline__ void team_barrier(int id)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kTeamThreads) : "memory");
+}
+
+// x: the role's state slice (3 components, 6 for role 2), advanced in place by one step of length dt
+template <int ROLE>
+__device__ __forceinline__ void quad12_step_team(double dt, int q, int bar_id, double (&x)[6], const double (&u)[4], double *scratch)
+{
+    constexpr int NC = team_role_count(ROLE);
+    const double h = dt / 5;
+    const double hh = h / 2.0;
+    const double h6 = h / 6.0;
+    double acc[NC], xs[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { acc[i] = 0.0; xs[i] = x[i]; }
+#pragma unroll 1
+    for (int ev = 0; ev < 20; ++ev) {
+        const int stage = ev & 3;
+        double *xsh = scratch + (ev & 1) * (12 * 32) + q;  // [12][32]: 0..2 v, 3..5 w, 6..11 sy cy sp cp sr cr
+        double sp, cp, sr, cr, icp = 0.0;
+        if constexpr (ROLE == 0) {
+            double sn3[3], cs3[3];
+            ode_sincos3(xs, sn3, cs3);
+            sp = sn3[1]; cp = cs3[1]; sr = sn3[2]; cr = cs3[2];
+            xsh[6 * 32] = sn3[0]; xsh[7 * 32] = cs3[0]; xsh[8 * 32] = sp; xsh[9 * 32] = cp; xsh[10 * 32] = sr; xsh[11 * 32] = cr;
+            icp = 1.0 / cp;  // issued before the barrier: the division completes in its shadow
+        } else if constexpr (ROLE == 2) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) xsh[i * 32] = xs[i];
+        }
+        team_barrier(bar_id);
+        double k[NC];
+        if constexpr (ROLE == 0) {
+            const double w0 = xsh[3 * 32], w1 = xsh[4 * 32], w2 = xsh[5 * 32];
+            const double tp = sp * icp;
+            const double wq = w1 * sr + w2 * cr;
+            k[0] = wq * icp;
+            k[1] = w1 * cr - w2 * sr;
+            k[2] = w0 + wq * tp;
+        } else if constexpr (ROLE == 1) {
+            const double sy = xsh[6 * 32], cy = xsh[7 * 32];
+            sp = xsh[8 * 32]; cp = xsh[9 * 32]; sr = xsh[10 * 32]; cr = xsh[11 * 32];
+            const double v0 = xsh[0], v1 = xsh[1 * 32], v2 = xsh[2 * 32];
+            const double srsp = sr * sp, crsp = cr * sp;
+            k[0] = v0 * (cy * cp) + v1 * (srsp * cy - sy * cr) + v2 * (sr * sy + crsp * cy);
+            k[1] = v0 * (sy * cp) + v1 * (srsp * sy + cr * cy) + v2 * (crsp * sy - sr * cy);
+            k[2] = v1 * (sr * cp) - v0 * sp + v2 * (cr * cp);
+        } else {
+            sp = xsh[8 * 32]; cp = xsh[9 * 32]; sr = xsh[10 * 32]; cr = xsh[11 * 32];
+            const double v0 = xs[0], v1 = xs[1], v2 = xs[2];
+            const double w0 = xs[3], w1 = xs[4], w2 = xs[5];
+            k[0] = v1 * w2 - v2 * w1 + kGravity * sp;
+            k[1] = v2 * w0 - v0 * w2 - kGravity * (sr * cp);
+            k[2] = kThrustGain * u[3] + v0 * w1 - v1 * w0 - kGravity * (cr * cp);
+            k[3] = kTauX * u[0] - kGyroX * (w1 * w2);
+            k[4] = kTauY * u[1] + kGyroY * (w0 * w2);
+            k[5] = kTauZ * u[2] - kGyroZ * (w0 * w1);
+        }
+        const double w = (stage == 0 || stage == 3) ? 1.0 : 2.0;
+        const double cst = (stage == 2) ? h : hh;
+        if (stage == 3) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                x[i] += h6 * (acc[i] + k[i]);
+                xs[i] = x[i];
+                acc[i] = 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                acc[i] = fma(w, k[i], acc[i]);
+                xs[i] = fma(cst, k[i], x[i]);
             }
         }
     }

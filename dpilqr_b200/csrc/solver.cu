@@ -317,6 +317,8 @@ struct LaunchTimer {
     }
 };
 
+constexpr int kStagedSearchMinProblems = 600;
+
 // ---- the driver loop -----------------------------------------------------------------------------
 static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *opts, const double *x0,
                             const double *U0, double *X, double *U, double *J, double *J_star, int32_t *iters,
@@ -360,6 +362,7 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
     fp.alpha[0] = 0.0;
     fp.n_list = B;
     fp.uniform_model = batch->model_hint - 1;
+    fp.exempt_cand = -1;
     LaunchTimer timer(opts->profile != 0, stream);
     timer.begin(DPILQR_K_ROLLOUT, B);
     rc = launch_forward(fp, B, stream);
@@ -414,7 +417,12 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
         ls.xc_stride = NA * xlen; ls.uc_stride = NA * ulen; ls.jc_stride = NA;
         ls.n_list = n_act;
         ls.uniform_model = batch->model_hint - 1;
-        const int bounds[4] = {0, NA < 1 ? NA : 1, NA < 3 ? NA : 3, NA};
+        ls.J_bound = opts->bounded_search ? w.Jstar : nullptr;
+        ls.exempt_cand = NA - 1;
+        // (for a few hundred problems the machine is far from full and a launch costs its latency whatever it
+        // carries: all the candidates go in one launch then)
+        const bool staged = n_act >= kStagedSearchMinProblems;
+        const int bounds[4] = {0, !staged ? NA : (NA < 1 ? NA : 1), !staged ? NA : (NA < 3 ? NA : 3), NA};
         const double expect[3] = {1.0, 0.45, 0.3};  // share of the active problems that reaches each stage (metric batch)
         const int32_t *list_in = act;
         const int32_t *count_in = w.n_active;
@@ -543,17 +551,11 @@ int dpilqr_rollout_linesearch(const dpilqr_batch *batch, const double *X, const 
     fp.xc_stride = (int64_t)n_alpha * (T + 1) * n; fp.uc_stride = (int64_t)n_alpha * T * m; fp.jc_stride = n_alpha;
     fp.n_list = batch->n_problems;
     fp.uniform_model = batch->model_hint - 1;
-    // the kernel takes up to kRolloutMaxThreads / a candidates of a problem per launch: wide teams go in chunks
-    int chunk = n_alpha;
-    while (chunk > 1 && chunk * batch->n_agents > 256) --chunk;
-    for (int k0 = 0; k0 < n_alpha; k0 += chunk) {
-        fp.alpha_first = k0;
-        fp.n_alpha = (n_alpha - k0 < chunk) ? n_alpha - k0 : chunk;
-        for (int k = 0; k < fp.n_alpha; ++k) fp.alpha[k] = alphas ? alphas[k0 + k] : kAlphaTable[k0 + k];
-        rc = launch_forward(fp, batch->n_problems, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
-    return DPILQR_OK;
+    fp.alpha_first = 0;
+    fp.exempt_cand = -1;
+    fp.n_alpha = n_alpha;
+    for (int k = 0; k < n_alpha; ++k) fp.alpha[k] = alphas ? alphas[k] : kAlphaTable[k];
+    return launch_forward(fp, batch->n_problems, (cudaStream_t)stream);
 }
 
 int dpilqr_linearize_quadraticize(const dpilqr_batch *batch, const double *X, const double *U, double *stage,

@@ -163,6 +163,12 @@ class CompiledBatch:
         self.t_radius = torch.as_tensor(np.array([sp.radius for sp in specs], dtype=np.float64)).to(dev)
         self.t_weights = torch.as_tensor(np.array([sp.weights for sp in specs], dtype=np.float64)).to(dev).contiguous()
         self.t_hasprox = torch.as_tensor(np.array([sp.has_prox for sp in specs], dtype=np.int32)).to(dev)
+        # the bounded line search needs every stage cost >= 0: PSD reference-cost matrices, non-negative weights
+        def _psd(M):
+            return bool(np.all(np.linalg.eigvalsh(0.5 * (M + M.T)) >= -1e-12 * max(1.0, float(np.abs(M).max()))))
+
+        self.costs_nonnegative = (all(_psd(Q) and _psd(R) and _psd(Qf) for Q, R, Qf in zip(Qs, Rs, Qfs))
+                                  and all(sp.weights[0] >= 0.0 and sp.weights[1] >= 0.0 for sp in specs))
         self.struct = self._make_struct(self.N)
         self.stage_stride = int(_native.lib().dpilqr_stage_stride(self.a, self.s, self.c))
 
@@ -266,12 +272,17 @@ class CompiledBatch:
         return L
 
     # ---------------------------------------------------------------- full solve
-    def solve(self, x0, U0, n_lqr_iter=50, tol=1e-3, t_kill=None, n_alpha=N_LS_ITER, trace=False, profile=False):
+    def solve(self, x0, U0, n_lqr_iter=50, tol=1e-3, t_kill=None, n_alpha=N_LS_ITER, trace=False, profile=False, bounded_search=True):
         """ilqrSolver.solve for the whole batch (reference control.py:150-225).
 
         ``x0`` [B,n] and ``U0`` [B,N,m] may be NumPy arrays, host (ideally pinned) or CUDA
         tensors.  Returns a dict of CUDA tensors: X, U, J (last tried cost), J_star, iters,
-        status (+ trace_alpha / trace_mu / trace_J when ``trace``) and ``total_iters``."""
+        status (+ trace_alpha / trace_mu / trace_J when ``trace``) and ``total_iters``.
+
+        ``bounded_search`` (default on, used only when every stage cost is provably >= 0): a candidate of the line
+        search stops rolling out once its accumulated cost exceeds the problem's best cost -- it is rejected already;
+        its entry of ``trace_J`` then reads ``_native.J_ABORTED``.  Accepted steps, iteration counts and all returned
+        trajectories and costs are those of the full search."""
         if n_lqr_iter < 0:
             raise ValueError("n_lqr_iter must be >= 0")
         x0 = self._dev(x0, (self.B, self.n))
@@ -288,7 +299,8 @@ class CompiledBatch:
             ta = self._empty(self.B, max(n_lqr_iter, 1), dtype=torch.int32)
             tm = self._empty(self.B, max(n_lqr_iter, 1))
             tj = self._empty(self.B, max(n_lqr_iter, 1), n_alpha)
-        opts = SolveOpts(int(n_lqr_iter), int(n_alpha), float(tol), float(t_kill) if t_kill else 0.0, int(bool(trace)), int(bool(profile)))
+        opts = SolveOpts(int(n_lqr_iter), int(n_alpha), float(tol), float(t_kill) if t_kill else 0.0, int(bool(trace)), int(bool(profile)),
+                         int(bool(bounded_search) and self.costs_nonnegative), 0)
         with torch.cuda.device(self.device):
             total = _native.check(lib.dpilqr_solve_batch(
                 ctypes.byref(self.struct), ctypes.byref(opts), _ptr(x0), _ptr(U0), _ptr(X), _ptr(U), _ptr(J), _ptr(Js),

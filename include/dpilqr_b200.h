@@ -99,7 +99,18 @@ typedef struct dpilqr_solve_opts {
     double t_kill;      /* <= 0: none.  Wall-clock seconds for the whole batch (documented deviation) */
     int32_t record_trace; /* 1: fill the per-iteration trace arrays */
     int32_t profile;      /* 1: time every kernel launch with CUDA events (see dpilqr_get_profile) */
+    int32_t bounded_search; /* 1: a line-search candidate stops rolling out as soon as its accumulated cost exceeds the
+                               best cost J* -- it is rejected already, because every remaining term is >= 0 -- and its
+                               cost reads DPILQR_J_ABORTED.  ONLY valid when (Q+Q^T), (R+R^T), (Qf+Qf^T) are positive
+                               semi-definite and both GameCost weights are >= 0 (the caller checks; the Python front
+                               door does).  Accepted steps, iteration counts and every returned number are unchanged:
+                               the last candidate, whose cost ilqrSolver.solve returns after a failed search
+                               (control.py:225), is always rolled out in full. */
+    int32_t reserved;
 } dpilqr_solve_opts;
+
+/* cost reported for a candidate stopped by bounded_search: "rejected, at least J*" */
+#define DPILQR_J_ABORTED 1.7976931348623157e308
 
 /* kernel kinds of the solve loop, index into dpilqr_profile */
 enum {

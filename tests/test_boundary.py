@@ -51,7 +51,7 @@ def test_struct_layout_matches_header(built_lib):
     from dpilqr_b200 import _native
 
     assert ctypes.sizeof(_native.BatchStruct) == 6 * 4 + 8 + 10 * 8 + 2 * 4
-    assert ctypes.sizeof(_native.SolveOpts) == 32
+    assert ctypes.sizeof(_native.SolveOpts) == 40
 
 
 def test_api_surface_matches_reference_namespace():

@@ -130,6 +130,7 @@ def test_solve_trace_vs_reference_golden(name):
     """Whole solve from the same inputs: iteration count, accepted step sizes, regularisation schedule, per-iteration
     accepted cost, final X / U / J."""
     import dpilqr_b200 as dp
+    from dpilqr_b200 import _native
 
     case = golden(f"solve_{name}.npz")
     solver = dp.ilqrSolver(product_problem(case), int(case["N"]))
@@ -148,7 +149,9 @@ def test_solve_trace_vs_reference_golden(name):
         if k >= 0:
             assert abs(tr["J_tried"][i, k] - case["trace_J"][i, k]) <= tol_i * abs(case["trace_J"][i, k]), i
             for j in range(k):  # rejected candidates that are not runaway rollouts
-                if case["trace_J"][i, j] < 1.5 * J_star:
+                if tr["J_tried"][i, j] == _native.J_ABORTED:  # stopped by the bounded line search: rejected for sure
+                    assert case["trace_J"][i, j] >= J_star * (1 - tol_i), (i, j)
+                elif case["trace_J"][i, j] < 1.5 * J_star:
                     assert abs(tr["J_tried"][i, j] - case["trace_J"][i, j]) <= 100 * tol_i * abs(case["trace_J"][i, j]), (i, j)
             J_star = float(case["trace_J"][i, k])
     if float(case["sens_X"]) < WELL_CONDITIONED:
@@ -216,6 +219,36 @@ def test_solve_distributed_vs_reference_golden(name):
     X2, U2, J2, info2 = dp.solve_distributed(prob, case["X_in"], case["U0"], float(case["radius_graph"]), None, None, False,
                                              n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]))
     assert np.array_equal(X2, X) and np.array_equal(U2, U) and J2 == J
+
+
+@pytest.mark.parametrize("name", ["quad12_a10_s2", "quad12_a3_s1", "cfg2_uni4_a5", "cfg3_q6q6h6", "misc_Bike5D_a3"])
+def test_bounded_line_search_changes_nothing_but_rejected_costs(name):
+    """The bounded line search stops a candidate once its accumulated cost has passed J* (it is rejected already):
+    accepted steps, iteration count, every returned trajectory and cost must be BITWISE those of the full search;
+    only the recorded costs of rejected candidates may read J_ABORTED."""
+    import dpilqr_b200 as dp
+    from dpilqr_b200 import _native
+
+    case = golden(f"solve_{name}.npz")
+    batch = dp.CompiledBatch([dp.spec_from_problem(product_problem(case))], int(case["N"]))
+    assert batch.costs_nonnegative
+    kw = dict(n_lqr_iter=int(case["n_lqr_iter"]), tol=float(case["tol"]), trace=True)
+    full = batch.solve(case["x0"][None], case["U0"][None], bounded_search=False, **kw)
+    fast = batch.solve(case["x0"][None], case["U0"][None], bounded_search=True, **kw)
+    for key in ("X", "U", "J", "J_star", "iters", "status", "trace_alpha", "trace_mu"):
+        assert torch_equal(full[key], fast[key]), key
+    tf, tb = full["trace_J"][0].cpu().numpy(), fast["trace_J"][0].cpu().numpy()
+    aborted = tb == _native.J_ABORTED
+    same = (tf == tb) | (np.isnan(tf) & np.isnan(tb))
+    assert np.all(same | aborted)
+    assert not np.any(aborted[:, -1])  # the last candidate is always rolled out in full (control.py:225)
+    print(f"{name}: {int(aborted.sum())} of {int((~np.isnan(tf)).sum())} tried candidates stopped early")
+
+
+def torch_equal(a, b):
+    import torch
+
+    return bool(torch.equal(a, b) or torch.equal(torch.nan_to_num(a.double(), nan=-1.0), torch.nan_to_num(b.double(), nan=-1.0)))
 
 
 def test_batch_equals_single_bitwise():
