@@ -38,7 +38,8 @@ from .dynamics import (
     UnicycleDynamics4D,
     linearize_finite_difference,
 )
-from .engine import CompiledBatch, ProblemSpec, bin_specs, solve_specs, spec_from_problem
+from .batched import LOG_HEADER, solve_distributed_round, solve_rhc_batch, trajectory_metrics
+from .engine import CompiledBatch, ProblemSpec, bin_specs, raise_for_status, solve_specs, spec_from_problem
 from .graphics import (
     eyeball_scenario,
     make_trajectory_gif,

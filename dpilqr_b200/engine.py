@@ -172,6 +172,40 @@ class CompiledBatch:
         self.struct = self._make_struct(self.N)
         self.stage_stride = int(_native.lib().dpilqr_stage_stride(self.a, self.s, self.c))
 
+    @classmethod
+    def from_tensors(cls, N, a, s, c, dt, t_model, t_ndims, t_cidx, t_Q, t_R, t_Qf, t_xf, t_radius, t_weights, t_hasprox,
+                     model_hint, costs_nonnegative, device):
+        """Descriptor built directly from device tensors (no per-problem Python objects): the batched DP-iLQR and
+        receding-horizon drivers derive the descriptors of their sub-batches with gathers on the device."""
+        self = cls.__new__(cls)
+        _native.require_device()
+        self.device = torch.device(device)
+        self.B, self.N = int(t_model.shape[0]), int(N)
+        self.a, self.s, self.c, self.dt = int(a), int(s), int(c), float(dt)
+        self.n, self.m = self.a * self.s, self.a * self.c
+        i32 = dict(dtype=torch.int32, device=self.device)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.t_model = t_model.to(**i32).contiguous()
+        self.t_ndims = t_ndims.to(**i32).contiguous()
+        self.t_cidx = t_cidx.to(**i32).contiguous()
+        self.t_Q, self.t_R, self.t_Qf = t_Q, t_R, t_Qf
+        self.t_xf = t_xf.to(**f64).contiguous()
+        self.t_radius = t_radius.to(**f64).contiguous()
+        self.t_weights = t_weights.to(**f64).contiguous()
+        self.t_hasprox = t_hasprox.to(**i32).contiguous()
+        self.model_hint = int(model_hint)
+        self.costs_nonnegative = bool(costs_nonnegative)
+        self.struct = self._make_struct(self.N)
+        self.stage_stride = int(_native.lib().dpilqr_stage_stride(self.a, self.s, self.c))
+        return self
+
+    def select(self, index, N=None):
+        """Sub-batch of the problems at ``index`` (a device int64 tensor), optionally with another horizon."""
+        return CompiledBatch.from_tensors(
+            self.N if N is None else N, self.a, self.s, self.c, self.dt, self.t_model[index], self.t_ndims[index], self.t_cidx[index],
+            self.t_Q, self.t_R, self.t_Qf, self.t_xf[index], self.t_radius[index], self.t_weights[index], self.t_hasprox[index],
+            self.model_hint, self.costs_nonnegative, self.device)
+
     def _make_struct(self, horizon):
         return BatchStruct(
             self.B, self.a, self.s, self.c, int(horizon), int(self.t_Q.shape[0]), self.dt,
