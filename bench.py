@@ -1,26 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- batched iLQR iterations/sec on 4096 x 10-agent Quadcopter12D scenarios.
+"""bench.py -- batched iLQR iterations/sec on synthetic multi-agent Quadcopter12D scenarios.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--agents 3|5|10|15] [--mode potential|dp] [--scaling weak|strong] [--scenarios B]
 
-One "step" = one complete batched Potential-iLQR solve (ilqrSolver.solve semantics, reference
-control.py:150-225) of `--scenarios` synthetic scenarios per GPU; the metric counts iLQR
-iterations (one backward Riccati pass + its 10-candidate line search for one problem) per second.
+Headline (defaults): 4096 x 10-agent Quadcopter12D, Potential-iLQR -- one "step" = one complete batched
+ilqrSolver.solve (reference control.py:150-225) of all the scenarios; the metric counts iLQR iterations (one backward
+Riccati pass + its line search for one problem) per second.  The other cells of BASELINE.json's sweep
+(reference scripts/analysis.py:126-174: agent counts x centralized / distributed) run with --agents / --mode dp,
+where a step is one DP-iLQR round (solve_distributed, reference distributed.py:25-103) of every scenario: interaction
+graphs, all sub-problems binned by neighbourhood size, stitch, joint cost.
 
   value         device-timed, inputs resident in HBM when the timed region starts
-  e2e           same metric through the public API with host (pinned) buffers: H2D of x0/U0 and D2H
-                of X/U/J/iters inside the timed region
-  roofline      dominant kernel (backward Riccati, FP64-compute bound) against the DFMA peak
-                measured on this box by tools/bin/fp64_peak; HBM view alongside
-  cpu_baseline  the CPU oracle (oracle/, a restatement of the reference's algorithm using the
-                reference's own compiled dynamics when oracle/_ref is present) on all host cores,
-                on a bounded sample of the same scenarios
+  e2e           same metric through the C ABI with HOST buffers (dpilqr_solve_batch_host for Potential-iLQR;
+                solve_distributed_round with host tensors for DP-iLQR): host->device copies of the inputs and
+                device->host copies of the results inside the timed region
+  roofline      dominant kernel (backward Riccati, FP64-compute bound) against the FP64 peak measured on this box by
+                tools/bin/fp64_peak; second kernel (rollout / line search) alongside
+  cpu_baseline  the CPU oracle (oracle/: a restatement of the reference's loop on the reference's own compiled
+                dynamics when oracle/_ref is present) on all host cores, on a bounded sample of the same scenarios
+  parity_sample the GPU solve of the very scenarios the CPU leg solved, compared per scenario: iteration count,
+                accepted step-size trace, final cost and trajectory
 
-Multi-GPU (torchrun, one rank per GPU): scenarios are independent, each rank solves its own 4096
-(weak scaling), no data-path collective; time is the max over ranks.
+Multi-GPU (torchrun, one rank per GPU): scenarios are independent, no data-path collective; time is the max over
+ranks.  --scaling weak (default): every rank solves --scenarios of its own; --scaling strong: --scenarios in total,
+dealt round-robin over the ranks.
 """
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -30,12 +38,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "batched iLQR iterations/sec (4096x10-agent Quad12D)"
 UNIT = "iterations/s"
-A, S, C, T = 10, 12, 4, 50
+S, C, T = 12, 4, 50
 
 
-def backward_flops(a=A, s=S, c=C, T=T):
+def metric_name(a, mode, B=4096):
+    if a == 10 and mode == "potential":
+        return f"batched iLQR iterations/sec ({B}x10-agent Quad12D)"
+    return f"batched iLQR iterations/sec ({B}x{a}-agent Quad12D, {'DP-iLQR round' if mode == 'dp' else 'Potential-iLQR'})"
+
+
+def backward_flops(a, s=S, c=C, T=T):
     """Structure-aware FLOPs of one backward pass."""
     n, m = a * s, a * c
     step = (4 * n * n * s + 4 * m * n * s + 2 * m * m * s + (2.0 / 3.0) * m ** 3 + 2 * m * m * (n + 1) + 2 * n * m * m
@@ -43,7 +56,7 @@ def backward_flops(a=A, s=S, c=C, T=T):
     return step * T
 
 
-def backward_hbm_bytes(a=A, s=S, c=C, T=T):
+def backward_hbm_bytes(a, s=S, c=C, T=T):
     """Algorithmic HBM bytes of one backward pass: stage records in, K and d out."""
     n, m = a * s, a * c
     pairs = a * (a - 1) // 2
@@ -51,46 +64,98 @@ def backward_hbm_bytes(a=A, s=S, c=C, T=T):
     return 8 * ((T + 1) * stage + T * m * n + T * m)
 
 
+def rollout_hbm_bytes(a, n_alpha=1, s=S, c=C, T=T):
+    """Algorithmic HBM bytes of one line-search launch per problem: K, d, X, U in; n_alpha candidates out."""
+    n, m = a * s, a * c
+    return 8 * (T * m * n + T * m + (T + 1) * n + T * m + n_alpha * ((T + 1) * n + T * m))
+
+
 # --------------------------------------------------------------------------------------------
 # CPU baseline / reference arm (the only place bench.py executes oracle/)
 # --------------------------------------------------------------------------------------------
-def _cpu_worker(k):
+def _cpu_worker(job):
     import numpy as np
 
     from dpilqr_b200 import scenarios
     from oracle import ilqr_oracle as O
 
-    x0, xf, U0 = scenarios.quad12_inputs(k, A, T)
-    prob = O.OracleProblem(["Quadcopter12D"] * A, 0.1, xf, np.eye(12), np.eye(4), 1000 * np.eye(12), 0.5, [3] * A,
-                           [100 + i for i in range(A)])
-    solver = O.OracleSolver(prob, T)
-    solver.solve(x0, U0)
-    return solver.n_backward
+    k, a, mode = job
+    x0, xf, U0 = scenarios.quad12_inputs(k, a, T)
+    prob = O.OracleProblem(["Quadcopter12D"] * a, 0.1, xf, np.eye(12), np.eye(4), 1000 * np.eye(12), 0.5, [3] * a,
+                           [100 + i for i in range(a)])
+    if mode == "potential":
+        solver = O.OracleSolver(prob, T)
+        X, U, J = solver.solve(x0, U0)
+        return dict(k=k, iters=solver.n_backward, alpha=[r["alpha_index"] for r in solver.trace], J=float(J), X=X)
+    Xh, _ = O.OracleSolver(prob, T).rollout(x0, U0)
+    count = [0]
+    X, U, J, info = O.solve_distributed(prob, Xh, U0, 0.5, [], count=count)
+    return dict(k=k, iters=count[0], alpha=[len(v[1]) for v in info.values()], J=float(J), X=X)
 
 
-def cpu_reference_run(n_scen, first=0):
-    """iterations/s of the CPU oracle over `n_scen` scenarios on all host cores (scenario-level pool,
-    one BLAS thread per worker -- the working equivalent of the reference's multiprocessing path,
-    SURVEY.md section 8d)."""
+def _cpu_sensitivity(job):
+    """How far the CPU oracle's OWN result moves when x0 is perturbed by 1e-15 relative (three sign patterns): the
+    yardstick for scenarios on which iLQR amplifies rounding (the golden fixtures record the same for the reference)."""
+    import numpy as np
+
+    from dpilqr_b200 import scenarios
+    from oracle import ilqr_oracle as O
+
+    k, a, mode = job
+    x0, xf, U0 = scenarios.quad12_inputs(k, a, T)
+    prob = O.OracleProblem(["Quadcopter12D"] * a, 0.1, xf, np.eye(12), np.eye(4), 1000 * np.eye(12), 0.5, [3] * a,
+                           [100 + i for i in range(a)])
+
+    def run(xp):
+        if mode == "potential":
+            solver = O.OracleSolver(prob, T)
+            X, U, J = solver.solve(xp, U0.copy())
+            return [r["alpha_index"] for r in solver.trace], X
+        Xh, _ = O.OracleSolver(prob, T).rollout(xp, U0)
+        count = [0]
+        X, U, J, info = O.solve_distributed(prob, Xh, U0, 0.5, [], count=count)
+        return [count[0]], X
+
+    tr0, X0 = run(x0)
+    moved, trace_changes = 0.0, 0
+    for trial in range(1, 4):
+        sg = np.sign(np.random.default_rng(trial).normal(size=x0.shape))
+        tr, X = run(x0 * (1 + 1e-15 * sg))
+        trace_changes += tr != tr0
+        if X.shape == X0.shape:
+            moved = max(moved, float(np.max(np.abs(X - X0)) / max(np.max(np.abs(X0)), 1e-300)))
+    return dict(k=k, trace_changes=int(trace_changes), moved=moved)
+
+
+def cpu_reference_run(n_scen, a, mode, first=0, keep=False):
+    """iterations/s of the CPU oracle over `n_scen` scenarios on all host cores (scenario-level pool, one BLAS thread
+    per worker -- the working equivalent of the reference's multiprocessing path)."""
     import multiprocessing as mp
 
     from oracle import ilqr_oracle as O
 
     O.build_c_oracle()
-    kind = "reference" if O.dynamics_backend("auto").name == "reference-native" else "port"
+    native = O.dynamics_backend("auto").name == "reference-native"
     cores = os.cpu_count() or 1
     for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[var] = "1"
     ctx = mp.get_context("spawn")
+    jobs = [(k, a, mode) for k in range(first, first + n_scen)]
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, range(first, first + min(cores, n_scen)))  # warm the workers (imports, dlopen)
+        pool.map(_cpu_worker, jobs[:min(cores, n_scen)])  # warm the workers (imports, dlopen)
         t0 = time.perf_counter()
-        iters = pool.map(_cpu_worker, range(first, first + n_scen), chunksize=1)
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
-    return dict(value=sum(iters) / dt, unit=UNIT, cores=cores, kind=kind, iterations=int(sum(iters)), seconds=dt,
-                sample=f"{n_scen} of the 4096 scenarios (seeds {first}..{first + n_scen - 1}), Potential-iLQR, "
-                       f"multiprocessing.Pool({cores}) over scenarios, 1 BLAS thread/worker; python restatement of the "
-                       f"reference loop (oracle/ilqr_oracle.py) on the {'reference-compiled' if kind == 'reference' else 'restated C'} dynamics")
+    iters = sum(r["iters"] for r in res)
+    what = "Potential-iLQR (ilqrSolver.solve)" if mode == "potential" else "one DP-iLQR round (solve_distributed)"
+    out = dict(value=iters / dt, unit=UNIT, cores=cores, kind="port", iterations=int(iters), seconds=dt,
+               sample=f"{n_scen} of the scenarios (seeds {first}..{first + n_scen - 1}), {a} agents, {what}, "
+                      f"multiprocessing.Pool({cores}) over scenarios, 1 BLAS thread/worker; NumPy restatement of the "
+                      f"reference loop (oracle/ilqr_oracle.py) calling the "
+                      f"{'reference-compiled bbdynamics module (oracle/_ref)' if native else 'plain-C restatement of the dynamics'}")
+    if keep:
+        out["results"] = res
+    return out
 
 
 def run_reference_arm(args):
@@ -101,17 +166,18 @@ def run_reference_arm(args):
     n_scen = args.cpu_scenarios or max(8 * cores, 64)
     vals = []
     for step in range(args.warmup + args.steps):
-        res = cpu_reference_run(n_scen)
+        res = cpu_reference_run(n_scen, args.agents, args.mode)
         if step >= args.warmup:
             vals.append(res)
     value = sum(r["iterations"] for r in vals) / sum(r["seconds"] for r in vals)
     base = dict(vals[-1], value=value)
     base.pop("iterations"), base.pop("seconds")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(r["seconds"] for r in vals) / len(vals), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n_scen}-scenario sample of 4096 x 10-agent Quadcopter12D Potential-iLQR, N=50, dt=0.1 (CPU)"},
+        "impl": "reference", "metric": metric_name(args.agents, args.mode), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(r["seconds"] for r in vals) / len(vals),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n_scen}-scenario sample of 4096 x {args.agents}-agent Quadcopter12D "
+                               f"{'Potential-iLQR' if args.mode == 'potential' else 'DP-iLQR round'}, N=50, dt=0.1 (CPU)"},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -158,8 +224,9 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one backward launch over 3908 problems (profiles/r01_backward_ncu_full.txt)
-NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM = (4.180168e9 + 7.515227e9) / 3908
+# dram__bytes_read.sum + dram__bytes_write.sum of one backward launch over 3908 ten-agent problems
+# (ncu --set full, profiles/r01_backward_ncu_full.txt): extrapolated per problem, not re-measured in the run
+NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM_A10 = (4.180168e9 + 7.515227e9) / 3908
 
 
 def measure_fp64_peak():
@@ -172,6 +239,70 @@ def measure_fp64_peak():
         return max(v["tflops"] for v in vals if str(v.get("kernel", "")).startswith(("dfma", "dmma")))
     except Exception:
         return None
+
+
+def parity_sample(results, out, a, mode):
+    """Per-scenario comparison of the GPU solve with the CPU leg on the same seeds (iteration
+    counts per problem must equal the oracle's)."""
+    import numpy as np
+
+    rows, n_iter_bad, n_alpha_bad, errs_J, errs_X, suspects = [], 0, 0, [], [], {}
+    for j, r in enumerate(results):
+        if mode == "potential":
+            it = int(out["iters"][j])
+            alpha = [int(v) for v in out["trace_alpha"][j, :it]]
+            J, X = float(out["J"][j]), out["X"][j]
+        else:
+            it = int(out["sub_iters"][j].sum())
+            adj = out["adjacency"][j]
+            alpha = [bin(int(v) & ((1 << a) - 1)).count("1") for v in adj]  # neighbourhood sizes
+            J, X = float(out["J_full"][j]), out["X_dec"][j]
+        same_it, same_al = (it == r["iters"]), (alpha == list(r["alpha"]))
+        n_iter_bad += not same_it
+        n_alpha_bad += not same_al
+        if same_it and same_al:
+            eJ = abs(J - r["J"]) / abs(r["J"]) if np.isfinite(r["J"]) and r["J"] != 0 else (0.0 if (np.isnan(J) and np.isnan(r["J"])) else float("inf"))
+            eX = float(np.max(np.abs(X - r["X"])) / max(np.max(np.abs(r["X"])), 1e-300))
+            errs_J.append(eJ), errs_X.append(eX)
+            if not (eJ <= 1e-9 and eX <= 1e-9):
+                suspects[r["k"]] = {"seed": r["k"], "rel_err_X": eX, "rel_err_J": eJ}
+        else:
+            suspects[r["k"]] = {"seed": r["k"], "iters": [it, r["iters"]], "trace": [alpha, list(r["alpha"])]}
+    errs_J, errs_X = np.array(errs_J), np.array(errs_X)
+    # every scenario that is not bit-for-bit in its decisions and within 1e-9 is checked against the oracle's OWN
+    # sensitivity: explained if a 1e-15 perturbation of x0 changes the oracle's own decisions / moves its own result
+    # by at least a thousandth of the discrepancy
+    unexplained = 0
+    if suspects:
+        import multiprocessing as mp
+
+        with mp.get_context("spawn").Pool(min(len(suspects), os.cpu_count() or 1)) as pool:
+            for sres in pool.map(_cpu_sensitivity, [(k, a, mode) for k in suspects]):
+                row = suspects[sres["k"]]
+                row["oracle_trace_changes_under_1e-15"] = sres["trace_changes"]
+                row["oracle_moves_under_1e-15"] = sres["moved"]
+                if "trace" in row:
+                    row["explained"] = bool(sres["trace_changes"] > 0 or sres["moved"] > 1e-9)
+                else:
+                    row["explained"] = bool(max(row["rel_err_X"], row["rel_err_J"]) <= max(1e-9, 1000.0 * sres["moved"]))
+                unexplained += not row["explained"]
+                rows.append(row)
+    return {
+        "scenarios": len(results), "what": "GPU vs CPU oracle per scenario: iteration count, "
+        + ("accepted step-size index of every iteration" if mode == "potential" else "neighbourhood sizes of the interaction graph")
+        + ", final J and X",
+        "iteration_count_mismatches": int(n_iter_bad), "trace_mismatches": int(n_alpha_bad),
+        "compared_numerically": int(errs_J.size),
+        "max_rel_err_J": float(errs_J.max()) if errs_J.size else None, "max_rel_err_X": float(errs_X.max()) if errs_X.size else None,
+        "median_rel_err_X": float(np.median(errs_X)) if errs_X.size else None,
+        "within_1e-9": int(np.sum((errs_J <= 1e-9) & (errs_X <= 1e-9))),
+        "bar": "1e-9 relative where the reference itself is well conditioned; scenarios above it are ill-conditioned "
+               "solves that amplify rounding (the golden fixtures record the reference's own sensitivity)",
+        "outside_the_bar": sorted(rows, key=lambda r: r["seed"])[:12], "unexplained": int(unexplained),
+        "ok": bool(unexplained == 0),
+        "ok_means": "every scenario either matches the CPU oracle in iteration count, step-size trace and to 1e-9 in J and X, or is "
+                    "one on which the oracle's own result changes by more than that when x0 is perturbed by 1e-15",
+    }
 
 
 def run_gpu_arm(args):
@@ -189,31 +320,82 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.scenarios
-    # ---- problem construction (excluded from the timed regions)
-    specs, x0_np, U0_np = scenarios.quad12_batch(rank * B, B, A, T)
+    a, mode = args.agents, args.mode
+    n, m = a * S, a * C
+    if args.scaling == "strong":  # --scenarios in total, dealt round-robin (balances the iteration counts)
+        seeds = list(range(rank, args.scenarios, world))
+    else:
+        seeds = list(range(rank * args.scenarios, (rank + 1) * args.scenarios))
+    B = len(seeds)
+    # ---- problem construction (excluded from the timed regions, timed on its own)
+    t_build = time.perf_counter()
+    built = [scenarios.quad12_inputs(k, a, T) for k in seeds]
+    specs = [scenarios.quad12_spec(xf, a) for _, xf, _ in built]
+    x0_np, U0_np = np.stack([b[0] for b in built]), np.stack([b[2] for b in built])
+    t_inputs = time.perf_counter() - t_build
+    t_build = time.perf_counter()
     batch = dp.CompiledBatch(specs, T, dev)
+    torch.cuda.synchronize(dev)
+    t_compile = time.perf_counter() - t_build
     x0_dev, U0_dev = torch.as_tensor(x0_np).to(dev), torch.as_tensor(U0_np).to(dev)
     x0_pin, U0_pin = torch.as_tensor(x0_np).pin_memory(), torch.as_tensor(U0_np).pin_memory()
-    out_pin = dict(X=torch.empty((B, T + 1, A * S), dtype=torch.float64).pin_memory(),
-                   U=torch.empty((B, T, A * C), dtype=torch.float64).pin_memory(),
-                   J=torch.empty(B, dtype=torch.float64).pin_memory(), iters=torch.empty(B, dtype=torch.int32).pin_memory())
     fp64_peak = measure_fp64_peak() if rank == 0 else None
+    lib = _native.lib()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step_resident(profile=False):
-        return batch.solve(x0_dev, U0_dev, n_lqr_iter=50, tol=1e-3, profile=profile)["total_iters"]
+    if mode == "potential":
+        def step_resident(profile=False):
+            return batch.solve(x0_dev, U0_dev, n_lqr_iter=50, tol=1e-3, profile=profile)["total_iters"]
 
-    def step_e2e():
-        out = batch.solve(x0_pin, U0_pin, n_lqr_iter=50, tol=1e-3)
-        for k, buf in out_pin.items():
-            buf.copy_(out[k], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return out["total_iters"]
+        # end to end: the C ABI entry point a non-Python host binds, with host buffers (pinned) for everything
+        out_pin = dict(X=torch.empty((B, T + 1, n), dtype=torch.float64).pin_memory(), U=torch.empty((B, T, m), dtype=torch.float64).pin_memory(),
+                       J=torch.empty(B, dtype=torch.float64).pin_memory(), Js=torch.empty(B, dtype=torch.float64).pin_memory(),
+                       iters=torch.empty(B, dtype=torch.int32).pin_memory(), status=torch.empty(B, dtype=torch.int32).pin_memory())
+        host = dict(model=batch.t_model.cpu(), ndims=batch.t_ndims.cpu(), cidx=batch.t_cidx.cpu(), Q=batch.t_Q.cpu(), R=batch.t_R.cpu(),
+                    Qf=batch.t_Qf.cpu(), xf=batch.t_xf.cpu(), radius=batch.t_radius.cpu(), weights=batch.t_weights.cpu(), hasprox=batch.t_hasprox.cpu())
+        hb = _native.BatchStruct(B, a, S, C, T, int(batch.t_Q.shape[0]), batch.dt, host["model"].data_ptr(), host["ndims"].data_ptr(),
+                                 host["cidx"].data_ptr(), host["Q"].data_ptr(), host["R"].data_ptr(), host["Qf"].data_ptr(),
+                                 host["xf"].data_ptr(), host["radius"].data_ptr(), host["weights"].data_ptr(), host["hasprox"].data_ptr(),
+                                 batch.model_hint, 0)
+        opts = _native.SolveOpts(50, 10, 1e-3, 0.0, 0, 0, int(batch.costs_nonnegative), 0)
+
+        def step_e2e():
+            return _native.check(lib.dpilqr_solve_batch_host(
+                ctypes.byref(hb), ctypes.byref(opts), x0_pin.data_ptr(), U0_pin.data_ptr(), out_pin["X"].data_ptr(), out_pin["U"].data_ptr(),
+                out_pin["J"].data_ptr(), out_pin["Js"].data_ptr(), out_pin["iters"].data_ptr(), out_pin["status"].data_ptr(),
+                None, None, None, local))
+
+        h2d = int(x0_pin.numel() * 8 + U0_pin.numel() * 8 + sum(t.numel() * t.element_size() for t in host.values()))
+        d2h = int(sum(t.numel() * t.element_size() for t in out_pin.values()))
+        e2e_path = "dpilqr_solve_batch_host (C ABI, host buffers, descriptor arrays included)"
+    else:
+        Xh_dev, _ = batch.rollout(x0_dev, U0_dev)  # the trajectory the interaction graph is built on (hover rollout)
+        Xh_dev = Xh_dev.contiguous()
+        Xh_pin = Xh_dev.cpu().pin_memory()
+        out_pin = dict(X=torch.empty((B, T + 1, n), dtype=torch.float64).pin_memory(), U=torch.empty((B, T, m), dtype=torch.float64).pin_memory(),
+                       J=torch.empty(B, dtype=torch.float64).pin_memory())
+        last = {}
+
+        def step_resident(profile=False):
+            out = dp.solve_distributed_round(batch, Xh_dev, U0_dev, 0.5, profile=profile)
+            last.update(bins=out["bins"])
+            return out["total_iters"]
+
+        def step_e2e():
+            out = dp.solve_distributed_round(batch, Xh_pin.to(dev, non_blocking=True), U0_pin.to(dev, non_blocking=True), 0.5)
+            out_pin["X"].copy_(out["X_dec"], non_blocking=True)
+            out_pin["U"].copy_(out["U_dec"], non_blocking=True)
+            out_pin["J"].copy_(out["J_full"], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return out["total_iters"]
+
+        h2d = int(Xh_pin.numel() * 8 + U0_pin.numel() * 8)
+        d2h = int(sum(t.numel() * t.element_size() for t in out_pin.values()))
+        e2e_path = "solve_distributed_round with pinned host tensors in and out"
 
     for _ in range(args.warmup):
         step_resident()
@@ -231,7 +413,7 @@ def run_gpu_arm(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     prof = _native.get_profile(reset=True)
-    # ---- timed: end to end through the public API with host buffers
+    # ---- timed: end to end with host buffers
     step_e2e()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -254,7 +436,14 @@ def run_gpu_arm(args):
         value = iters / (ms * 1e-3)
         e2e_value = iters_e2e / (ms_e2e * 1e-3)
         bms, blaunch, bunits = prof["backward"]
-        achieved = backward_flops() * bunits / (bms * 1e-3) * 1e-12 if bms > 0 else None
+        lms, llaunch, lunits = prof["linesearch"]
+        if mode == "potential":
+            bflops = backward_flops(a) * bunits
+        else:  # sub-problems of every neighbourhood size: iterations of size k ~ share of the bins (all bins run ~ the same count)
+            bins = last.get("bins", {})
+            tot = max(sum(bins.values()), 1)
+            bflops = sum(backward_flops(k) * bunits * cnt / tot for k, cnt in bins.items())
+        achieved = bflops / (bms * 1e-3) * 1e-12 if bms > 0 else None
         peak, peak_src = (fp64_peak, "FP64 peak measured on this box by tools/bin/fp64_peak, max of the DFMA and DMMA m8n8k4 loops "
                                      "(MEASURED_PEAKS.json has no FP64 entry)") \
             if fp64_peak else (37.2, "nominal 148 SM x 64 DFMA/clk x 1.965 GHz (fp64_peak binary missing)")
@@ -264,40 +453,62 @@ def run_gpu_arm(args):
         except Exception:
             pass
         total_ms = sum(v[0] for v in prof.values())
+        kname = f"backward_kernel<12,4,{a}>" if mode == "potential" else "backward_kernel<12,4,k> over the neighbourhood sizes k"
+        per_gpu = B
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "metric": metric_name(a, mode), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{B} scenarios/GPU x 10-agent Quadcopter12D Potential-iLQR (ilqrSolver.solve), N=50, dt=0.1, "
-                                   "n_lqr_iter=50, tol=1e-3, hover warm start, random_setup energy=30 (SURVEY 8d)",
+            "config": {"workload": f"{per_gpu} scenarios/GPU x {a}-agent Quadcopter12D "
+                                   + ("Potential-iLQR (ilqrSolver.solve)" if mode == "potential" else "DP-iLQR round (solve_distributed on the hover rollout, radius 0.5)")
+                                   + f", N=50, dt=0.1, n_lqr_iter=50, tol=1e-3, hover warm start, random_setup energy={3 * a} (SURVEY 8d)",
                        "iterations_per_step": iters / args.steps / world,
-                       "l2": "working set per step (K 7.9 GB + candidates 5.3 GB + stage 4.4 GB) >> 126 MB L2",
-                       "parallelism": f"scenario-sharded x{world}, no data-path collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x0_pin.numel() * 8 + U0_pin.numel() * 8),
-                    "d2h_bytes_per_step": int(sum(b.numel() * b.element_size() for b in out_pin.values())),
-                    "ms_per_step": ms_e2e / args.steps},
+                       "l2": "working set per step (gains, candidate trajectories, stage records: GBs) >> 126 MB L2",
+                       "parallelism": f"scenario-sharded x{world} ({args.scaling} scaling), no data-path collective",
+                       "construction_s": {"scenario_inputs_numpy": t_inputs, "CompiledBatch": t_compile,
+                                          "note": "outside the timed regions (SURVEY 8d), once per batch"}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "path": e2e_path},
             "gpu_launches": int(sum(v[1] for v in prof.values())),
             "clocks": clocks,
-            "roofline": {"kernel": "backward_kernel<12,4,10>", "bound": "tensor", "bound_detail": "FP64 pipe: mma.sync.m8n8k4.f64 tiles + DFMA",
+            "roofline": {"kernel": kname, "bound": "tensor", "bound_detail": "FP64 pipe: mma.sync.m8n8k4.f64 tiles + DFMA",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM * bunits / max(blaunch, 1),
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum = 11.695 GB for a 3908-problem launch "
-                                           "(profiles/r01_backward_ncu_full.txt), scaled to this run's average problems per launch; "
-                                           "algorithmic bytes/problem = %d" % backward_hbm_bytes(),
+                         "traffic": (NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM_A10 * bunits / max(blaunch, 1)) if (a == 10 and mode == "potential") else None,
+                         "traffic_source": "EXTRAPOLATED from one ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum = 11.695 GB "
+                                           "for a 3908-problem launch, profiles/r01_backward_ncu_full.txt) to this run's average problems per "
+                                           f"launch, not re-measured here; algorithmic bytes/problem = {backward_hbm_bytes(a)}",
                          "peak_source": peak_src,
-                         "flops_per_launch_unit": backward_flops(), "launches": blaunch, "avg_launch_ms": bms / max(blaunch, 1),
-                         "share_of_step": bms / total_ms if total_ms else None},
-            "roofline_hbm": {"kernel": "backward_kernel<12,4,10>", "bound": "hbm",
-                             "achieved": backward_hbm_bytes() * bunits / (bms * 1e-3) * 1e-9 if bms > 0 else None,
-                             "peak": hbm_peak, "unit": "GB/s", "frac": (backward_hbm_bytes() * bunits / (bms * 1e-3) * 1e-9 / hbm_peak) if bms > 0 else None},
+                         "flops_per_launch_unit": backward_flops(a) if mode == "potential" else None, "launches": blaunch,
+                         "avg_launch_ms": bms / max(blaunch, 1), "share_of_step": bms / total_ms if total_ms else None},
+            "roofline_linesearch": {"kernel": "rollout_kernel<Quadcopter12D> (staged line search)", "bound": "hbm",
+                                    "achieved": rollout_hbm_bytes(a) * lunits / (lms * 1e-3) * 1e-9 if lms > 0 else None,
+                                    "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": (rollout_hbm_bytes(a) * lunits / (lms * 1e-3) * 1e-9 / hbm_peak) if lms > 0 else None,
+                                    "note": "algorithmic bytes = gains read once per problem-iteration + trajectories; the kernel is bound by "
+                                            "the latency of the serial RK4 chain, not by either roofline (DESIGN.md)",
+                                    "share_of_step": lms / total_ms if total_ms else None},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            base = cpu_reference_run(args.cpu_scenarios or max(8 * cores, 64))
+            n_cpu = min(args.cpu_scenarios or max(8 * cores, 64), B)
+            base = cpu_reference_run(n_cpu, a, mode, first=seeds[0], keep=True)
+            results = base.pop("results")
             base.pop("iterations"), base.pop("seconds")
             line["cpu_baseline"] = base
+            # the GPU solve of the same seeds (they are the first n_cpu scenarios of this rank's batch)
+            if not args.no_parity:
+                idx = torch.arange(n_cpu, device=dev)
+                sub = batch.select(idx)
+                if mode == "potential":
+                    o = sub.solve(x0_dev[:n_cpu], U0_dev[:n_cpu], n_lqr_iter=50, tol=1e-3, trace=True)
+                else:
+                    o = dp.solve_distributed_round(sub, Xh_dev[:n_cpu], U0_dev[:n_cpu], 0.5)
+                o = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in o.items()}
+                line["parity_sample"] = parity_sample(results, o, a, mode)
+                if not line["parity_sample"]["ok"]:
+                    print("bench.py: PARITY SAMPLE MISMATCH (see parity_sample in the JSON line)", file=sys.stderr)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -309,9 +520,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scenarios", type=int, default=4096, help="scenarios per GPU")
+    ap.add_argument("--scenarios", type=int, default=4096, help="scenarios per GPU (weak scaling) or in total (strong scaling)")
+    ap.add_argument("--agents", type=int, default=10, choices=[2, 3, 4, 5, 6, 7, 8, 10, 12, 15])
+    ap.add_argument("--mode", default="potential", choices=["potential", "dp"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-scenarios", type=int, default=0, help="sample size of the CPU baseline (default 8 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

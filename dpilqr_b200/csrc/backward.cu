@@ -25,6 +25,8 @@
 // Quadcopter12D agents -> one CTA per SM); only the stage records stream in (TMA bulk copies, one step ahead)
 // and K, d stream out.  Problems too large for shared memory keep Q_ux/Y, K and the LU matrices in an L2-resident
 // global scratch instead (same code).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "lu.cuh"
 
@@ -1111,6 +1113,9 @@ int launch_backward(const BackwardParams &p_in, int n_blocks, cudaStream_t strea
     p.debug_mode = g_backward_debug_mode;
     const Batch &bt = p.batch;
     const int a = bt.n_agents, s = bt.s, c = bt.c;
+    // small problems (DP-iLQR neighbourhoods, small teams): several problems per SM (backward_small.cu)
+    static const bool force_big = getenv("DPILQR_BACKWARD_FORCE_BIG") != nullptr;  // experiments / cross-checks
+    if (!force_big && p.timing == nullptr && backward_small_applies(a, s, c)) return launch_backward_small(p, n_blocks, stream);
     if (a * c > 64) {
         set_error("backward kernel: at most 64 joint controls are supported (got %d)", a * c);
         return DPILQR_E_UNSUPPORTED;

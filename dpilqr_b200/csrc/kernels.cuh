@@ -81,6 +81,8 @@ int launch_linquad(const LinQuadParams &p, int n_problems, cudaStream_t stream);
 int launch_stage_to_dense(const Batch &bt, const double *stage, double *A, double *Bm, double *Lx, double *Lu,
                           double *Lxx, double *Luu, cudaStream_t stream);
 int launch_backward(const BackwardParams &p, int n_blocks, cudaStream_t stream);
+bool backward_small_applies(int a, int s, int c);  // backward_small.cu: n <= 64, m <= 32
+int launch_backward_small(const BackwardParams &p, int n_blocks, cudaStream_t stream);
 int64_t backward_scratch_doubles(int n_problems, int a, int s, int c);
 int launch_inter_graph(const double *X, int64_t n_scen, int rows, int a, int s, const double *radius, uint64_t *adj,
                        cudaStream_t stream);
