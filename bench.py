@@ -94,8 +94,10 @@ def _cpu_worker(job):
 
 
 def _cpu_sensitivity(job):
-    """How far the CPU oracle's OWN result moves when x0 is perturbed by 1e-15 relative (three sign patterns): the
-    yardstick for scenarios on which iLQR amplifies rounding (the golden fixtures record the same for the reference)."""
+    """How far the CPU oracle's OWN result moves (a) when x0 is perturbed by 1e-15 relative (three sign patterns) and
+    (b) when its backward pass evaluates the same formulas in another, equally valid floating-point order
+    (OracleSolver.arith): the yardstick for scenarios on which iLQR amplifies rounding (the golden fixtures record (a)
+    for the unmodified reference)."""
     import numpy as np
 
     from dpilqr_b200 import scenarios
@@ -106,25 +108,30 @@ def _cpu_sensitivity(job):
     prob = O.OracleProblem(["Quadcopter12D"] * a, 0.1, xf, np.eye(12), np.eye(4), 1000 * np.eye(12), 0.5, [3] * a,
                            [100 + i for i in range(a)])
 
-    def run(xp):
+    def run(xp, arith=0):
         if mode == "potential":
             solver = O.OracleSolver(prob, T)
+            solver.arith = arith
             X, U, J = solver.solve(xp, U0.copy())
-            return [r["alpha_index"] for r in solver.trace], X
+            return [r["alpha_index"] for r in solver.trace], X, float(J)
         Xh, _ = O.OracleSolver(prob, T).rollout(xp, U0)
         count = [0]
         X, U, J, info = O.solve_distributed(prob, Xh, U0, 0.5, [], count=count)
-        return [count[0]], X
+        return [count[0]], X, float(J)
 
-    tr0, X0 = run(x0)
-    moved, trace_changes = 0.0, 0
-    for trial in range(1, 4):
-        sg = np.sign(np.random.default_rng(trial).normal(size=x0.shape))
-        tr, X = run(x0 * (1 + 1e-15 * sg))
+    tr0, X0, J0 = run(x0)
+    moved, moved_J, trace_changes = 0.0, 0.0, 0
+    trials = [(x0 * (1 + 1e-15 * np.sign(np.random.default_rng(trial).normal(size=x0.shape))), 0) for trial in range(1, 4)]
+    if mode == "potential":
+        trials += [(x0, 1), (x0, 2)]
+    for xp, arith in trials:
+        tr, X, J = run(xp, arith)
         trace_changes += tr != tr0
-        if X.shape == X0.shape:
+        if X.shape == X0.shape and tr == tr0:
             moved = max(moved, float(np.max(np.abs(X - X0)) / max(np.max(np.abs(X0)), 1e-300)))
-    return dict(k=k, trace_changes=int(trace_changes), moved=moved)
+            if np.isfinite(J) and np.isfinite(J0) and J0 != 0:
+                moved_J = max(moved_J, abs(J - J0) / abs(J0))
+    return dict(k=k, trace_changes=int(trace_changes), moved=moved, moved_J=moved_J)
 
 
 def cpu_reference_run(n_scen, a, mode, first=0, keep=False):
@@ -270,8 +277,8 @@ def parity_sample(results, out, a, mode):
             suspects[r["k"]] = {"seed": r["k"], "iters": [it, r["iters"]], "trace": [alpha, list(r["alpha"])]}
     errs_J, errs_X = np.array(errs_J), np.array(errs_X)
     # every scenario that is not bit-for-bit in its decisions and within 1e-9 is checked against the oracle's OWN
-    # sensitivity: explained if a 1e-15 perturbation of x0 changes the oracle's own decisions / moves its own result
-    # by at least a thousandth of the discrepancy
+    # sensitivity: explained if a 1e-15 perturbation of x0 or an equally valid evaluation order of the backward pass
+    # changes the oracle's own decisions / moves its own result by at least a tenth of the discrepancy
     unexplained = 0
     if suspects:
         import multiprocessing as mp
@@ -279,12 +286,14 @@ def parity_sample(results, out, a, mode):
         with mp.get_context("spawn").Pool(min(len(suspects), os.cpu_count() or 1)) as pool:
             for sres in pool.map(_cpu_sensitivity, [(k, a, mode) for k in suspects]):
                 row = suspects[sres["k"]]
-                row["oracle_trace_changes_under_1e-15"] = sres["trace_changes"]
-                row["oracle_moves_under_1e-15"] = sres["moved"]
+                row["oracle_trace_changes_when_perturbed"] = sres["trace_changes"]
+                row["oracle_X_moves_when_perturbed"] = sres["moved"]
+                row["oracle_J_moves_when_perturbed"] = sres["moved_J"]
                 if "trace" in row:
                     row["explained"] = bool(sres["trace_changes"] > 0 or sres["moved"] > 1e-9)
                 else:
-                    row["explained"] = bool(max(row["rel_err_X"], row["rel_err_J"]) <= max(1e-9, 1000.0 * sres["moved"]))
+                    row["explained"] = bool(row["rel_err_X"] <= max(1e-9, 10.0 * sres["moved"])
+                                            and row["rel_err_J"] <= max(1e-9, 10.0 * sres["moved_J"]))
                 unexplained += not row["explained"]
                 rows.append(row)
     return {
@@ -301,7 +310,8 @@ def parity_sample(results, out, a, mode):
         "outside_the_bar": sorted(rows, key=lambda r: r["seed"])[:12], "unexplained": int(unexplained),
         "ok": bool(unexplained == 0),
         "ok_means": "every scenario either matches the CPU oracle in iteration count, step-size trace and to 1e-9 in J and X, or is "
-                    "one on which the oracle's own result changes by more than that when x0 is perturbed by 1e-15",
+                    "one on which the oracle's own decisions change, or its own X / J move by at least a tenth of the discrepancy, when x0 is "
+                    "perturbed by 1e-15 or its backward pass is evaluated in another equally valid floating-point order",
     }
 
 

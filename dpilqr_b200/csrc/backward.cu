@@ -314,6 +314,23 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         if ((p.debug_mode & 256) && t == T - 1) lu_experiment(28);
         {
             DPILQR_PHASE_IDS
+        // Symmetrise the diagonal blocks, P <- (P + P^T)/2 (control.py:146-147).  They are the only part of P stored on
+        // both sides of the diagonal, and phases B and F round the two triangles independently: the antisymmetric
+        // residue is not damped by the recursion (it propagates with the open-loop A^T . A and grew by about 12 % per
+        // time step on Quadcopter12D, costing two to three digits of K and d at t = 0).
+        {
+            constexpr int NPAIR = S * (S - 1) / 2;
+            for (int k = tid; k < a * NPAIR; k += nthr) {
+                const int i = k / NPAIR;
+                int r = 0, rem = k - i * NPAIR;
+                while (rem >= S - 1 - r) { rem -= S - 1 - r; ++r; }
+                const int cc = r + 1 + rem;
+                double *blk = Pb + (size_t)blk_index(i, i) * PBS;
+                const double v = 0.5 * (blk[r * S + cc] + blk[cc * S + r]);
+                blk[r * S + cc] = v;
+                blk[cc * S + r] = v;
+            }
+        }
         // Regularise P in place for phase A (P + mu I, control.py:134-135); the plain diagonal waits in pq (free until
         // phase E) and is put back before phase B, which needs the unregularised P.
         for (int k = (p.debug_mode & 8) ? n : tid; k < n; k += nthr) {
@@ -1131,7 +1148,8 @@ int launch_backward(const BackwardParams &p_in, int n_blocks, cudaStream_t strea
         return DPILQR_E_INVALID;
     }
     if (s == 12 && c == 4) {
-        if (a == 10 && !plan.use_global_scratch) {
+        static const bool force_generic = getenv("DPILQR_BACKWARD_FORCE_GENERIC") != nullptr;  // experiments / cross-checks
+        if (a == 10 && !plan.use_global_scratch && !force_generic) {
             if (p.timing != nullptr) return launch_typed<12, 4, 10, false, true>(p, n_blocks, plan, stream);
             return launch_typed<12, 4, 10, false>(p, n_blocks, plan, stream);
         }

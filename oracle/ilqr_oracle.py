@@ -396,6 +396,10 @@ class OracleSolver:
         self.trace = []  # one dict per outer iteration
         self.n_backward = 0
         self.cond_log = None  # set to a list to record cond(Q_uu) of every step of every backward pass
+        # 0: the reference's own evaluation order.  1, 2, ...: the SAME formulas in another, equally valid floating-point
+        # order (products re-associated, the linear system handed to LAPACK with its unknowns permuted) -- never a
+        # parity target, only the yardstick for how far rounding alone moves the reference's result on a scenario
+        self.arith = 0
 
     def rollout(self, x0, U):
         """_rollout (control.py:80-93)."""
@@ -443,6 +447,19 @@ class OracleSolver:
             Q_ux = L_ux + B.T @ (P + reg) @ A
             if self.cond_log is not None:
                 self.cond_log.append(np.linalg.cond(Q_uu))
+            if self.arith:
+                Pr = P + reg
+                Q_xx = L_xx + A.T @ (P @ A)
+                Q_uu = L_uu + B.T @ (Pr @ B)
+                Q_ux = L_ux + B.T @ (Pr @ A)
+                perm = np.random.default_rng(self.arith).permutation(n_u)
+                Mp = Q_uu[np.ix_(perm, perm)]
+                K[t][perm] = -np.linalg.solve(Mp, Q_ux[perm])
+                d[t][perm] = -np.linalg.solve(Mp, Q_u[perm])
+                p = Q_x + K[t].T @ Q_uu @ d[t] + K[t].T @ Q_u + Q_ux.T @ d[t]
+                P = Q_xx + K[t].T @ Q_uu @ K[t] + K[t].T @ Q_ux + Q_ux.T @ K[t]
+                P = 0.5 * (P + P.T)
+                continue
             K[t] = -np.linalg.solve(Q_uu, Q_ux)
             d[t] = -np.linalg.solve(Q_uu, Q_u)
             p = Q_x + K[t].T @ Q_uu @ d[t] + K[t].T @ Q_u + Q_ux.T @ d[t]
@@ -477,7 +494,7 @@ class OracleSolver:
             rec = {"mu": self.mu, "J_tried": []}
             K, d = self.backward_pass(X, U)
             if keep_gains:
-                rec["K"], rec["d"] = K, d
+                rec["K"], rec["d"], rec["X"], rec["U"] = K, d, X, U
             for k, alpha in enumerate(alphas):
                 Xn, Un, J = self.forward_pass(X, U, K, d, alpha)
                 rec["J_tried"].append(J)

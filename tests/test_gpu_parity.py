@@ -332,3 +332,23 @@ def test_metric_scale_properties():
         acc = [tj[k, i, ta[k, i]] for i in range(iters[k]) if ta[k, i] >= 0]
         assert all(b < a for a, b in zip([c["J0"]] + acc[:-1], acc))
     assert np.all((status & (16 | 32 | 64)) != 0)
+
+
+@pytest.mark.parametrize("name", ["quad12_a10_s0", "quad12_a10_s1", "quad12_a10_s2", "quad12_a5_s0", "quad12_a3_s0"])
+def test_backward_error_does_not_grow_along_the_recursion(name):
+    """The reference symmetrises P after every step (control.py:146-147).  The diagonal blocks of P are the only part this
+    kernel stores on both sides of the diagonal; left unsymmetrised their antisymmetric rounding residue grows about
+    12 % per time step on Quadcopter12D (open-loop A^T . A) and costs two to three digits of the gains at t = 0, the END
+    of the recursion.  With the symmetrisation the gains of the reference's last iterate agree to a few 1e-14."""
+    import dpilqr_b200 as dp
+
+    case = golden(f"solve_{name}.npz")
+    batch = dp.CompiledBatch([dp.spec_from_problem(product_problem(case))], int(case["N"]))
+    i = len(case["trace_mu"]) - 1
+    stage, _ = batch.linearize_quadraticize(case["iter_X"][i][None], case["iter_U"][i][None])
+    K, d, _ = batch.backward(stage, float(case["trace_mu"][i]))
+    eK = rel_err(K[0].cpu().numpy()[case["K_first_steps"]], case["K_last_iter"])
+    d_gpu, d_ref = d[0].cpu().numpy(), case["d_last_iter"]
+    e0 = rel_err(d_gpu[0], d_ref[0])
+    print(f"{name}: K[t=0] err {eK:.1e}  d[t=0] err {e0:.1e}  d all steps {rel_err(d_gpu, d_ref):.1e}")
+    assert eK < 5e-13 and e0 < 5e-13
