@@ -39,7 +39,7 @@ from .dynamics import (
     linearize_finite_difference,
 )
 from .batched import LOG_HEADER, solve_distributed_round, solve_rhc_batch, trajectory_metrics
-from .engine import CompiledBatch, ProblemSpec, bin_specs, raise_for_status, solve_specs, spec_from_problem
+from .engine import CompiledBatch, ProblemSpec, SolvePipeline, bin_specs, raise_for_status, solve_specs, spec_from_problem
 from .graphics import (
     eyeball_scenario,
     make_trajectory_gif,

@@ -1102,11 +1102,8 @@ template <int S, int C, int AT, bool GLOBAL, bool TIMED = false>
 static int launch_typed(const BackwardParams &p, int n_blocks, const BackwardPlan &plan, cudaStream_t stream)
 {
     auto kernel = backward_kernel<S, C, AT, GLOBAL, TIMED>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    // per launch: the attribute belongs to the device / context, and callers may drive several devices and threads
+    DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kernel<<<n_blocks, plan.threads, plan.smem_bytes, stream>>>(p);
     DPILQR_CUDA(cudaGetLastError());
     return DPILQR_OK;

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <vector>
 
@@ -319,14 +320,82 @@ struct LaunchTimer {
 
 constexpr int kStagedSearchMinProblems = 600;
 
+// ---- several solves in flight on one device ------------------------------------------------------
+// A solve has a BULK (thousands of active problems: every launch fills the machine) and a TAIL (the few problems that
+// need many more iterations than the rest: tens of launches of a handful of CTAs, each costing its full latency with
+// most SMs idle -- a tenth of the time of the metric batch for 1.5 % of its work).  Host threads that call the solver
+// concurrently (one stream each) take turns for the bulk -- the token below -- and run their tails on a high-priority
+// stream beside the next caller's bulk, where they cost their work instead of their latency.  A single caller sees no
+// difference.
+constexpr int kBulkMinProblems = kStagedSearchMinProblems;
+constexpr int kMaxDevices = 64;
+
+struct BulkGate {
+    std::mutex m;
+    std::condition_variable cv;
+    bool busy = false;
+};
+static BulkGate g_bulk_gate[kMaxDevices];
+
+struct BulkToken {
+    BulkGate *gate = nullptr;
+    void acquire(int device)
+    {
+        if (device < 0 || device >= kMaxDevices) return;
+        gate = &g_bulk_gate[device];
+        std::unique_lock<std::mutex> lk(gate->m);
+        gate->cv.wait(lk, [&] { return !gate->busy; });
+        gate->busy = true;
+    }
+    void release()
+    {
+        if (!gate) return;
+        {
+            std::lock_guard<std::mutex> lk(gate->m);
+            gate->busy = false;
+        }
+        gate->cv.notify_one();
+        gate = nullptr;
+    }
+    ~BulkToken() { release(); }
+};
+
+// Per host thread and device: the high-priority stream of the tail, the events that tie it to the caller's stream, and
+// the pinned word the active count is read back into (never freed: a few bytes and one stream per calling thread).
+struct ThreadContext {
+    int device = -1;
+    cudaStream_t tail = nullptr, host = nullptr;
+    cudaEvent_t ev = nullptr;
+    int32_t *h_count = nullptr;
+};
+static thread_local ThreadContext t_ctx;
+
+static int thread_context(ThreadContext **out)
+{
+    int device = -1;
+    DPILQR_CUDA(cudaGetDevice(&device));
+    if (t_ctx.device != device) {
+        int lo = 0, hi = 0;
+        DPILQR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi is the numerically lowest = greatest priority
+        DPILQR_CUDA(cudaStreamCreateWithPriority(&t_ctx.tail, cudaStreamNonBlocking, hi));
+        DPILQR_CUDA(cudaStreamCreateWithFlags(&t_ctx.host, cudaStreamNonBlocking));
+        DPILQR_CUDA(cudaEventCreateWithFlags(&t_ctx.ev, cudaEventDisableTiming));
+        if (!t_ctx.h_count) DPILQR_CUDA(cudaMallocHost(&t_ctx.h_count, 64));
+        t_ctx.device = device;
+    }
+    *out = &t_ctx;
+    return DPILQR_OK;
+}
+
 // ---- the driver loop -----------------------------------------------------------------------------
 static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *opts, const double *x0,
                             const double *U0, double *X, double *U, double *J, double *J_star, int32_t *iters,
                             int32_t *status, int32_t *trace_alpha, double *trace_mu, double *trace_J, void *workspace,
-                            int64_t workspace_bytes, cudaStream_t stream)
+                            int64_t workspace_bytes, cudaStream_t user_stream)
 {
     int rc = validate_batch(batch);
     if (rc) return rc;
+    cudaStream_t stream = user_stream;
     if (!opts || !x0 || !U0 || !X || !U || !iters || !status || !workspace) {
         set_error("dpilqr_solve_batch: null argument");
         return DPILQR_E_INVALID;
@@ -350,6 +419,10 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
     }
     if (!opts->record_trace) trace_alpha = nullptr;
     const int64_t xlen = (T + 1) * n, ulen = T * m;
+    ThreadContext *ctx = nullptr;
+    if ((rc = thread_context(&ctx))) return rc;
+    BulkToken token;
+    if (B >= kBulkMinProblems) token.acquire(ctx->device);
 
     // rollout of the warm start into candidate buffer 1, slot 0 (control.py:164)
     ForwardParams fp{};
@@ -373,13 +446,22 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
                                                           trace_J, n_iter, NA);
     DPILQR_CUDA(cudaGetLastError());
 
-    int32_t *h_count = nullptr;
-    DPILQR_CUDA(cudaMallocHost(&h_count, sizeof(int32_t)));
+    int32_t *h_count = ctx->h_count;
     *h_count = B;
     int64_t total_iters = 0;
     int n_act = B;
+    bool in_tail = false;
     const auto t0 = std::chrono::steady_clock::now();
     for (int it = 0; it < n_iter && n_act > 0; ++it) {
+        if (!in_tail && n_act < kBulkMinProblems) {
+            // the tail: hand the bulk token to the next caller and move to the high-priority stream
+            token.release();
+            if ((rc = check_cuda(cudaEventRecord(ctx->ev, stream), "tail event"))) break;
+            if ((rc = check_cuda(cudaStreamWaitEvent(ctx->tail, ctx->ev, 0), "tail wait"))) break;
+            stream = ctx->tail;
+            timer.stream = stream;
+            in_tail = true;
+        }
         const int cur = (it + 1) & 1, nxt = it & 1;
         const int32_t *act = w.active[it & 1];
         int32_t *act_out = w.active[(it + 1) & 1];
@@ -466,24 +548,81 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
             }
         }
     }
-    cudaFreeHost(h_count);
-    if (rc) return rc;
+    token.release();
+    if (rc) {
+        cudaStreamSynchronize(stream);
+        timer.flush();
+        return rc;
+    }
     gather_result_kernel<<<B, 128, 0, stream>>>(B, xlen, ulen, NA, w.candX[0], w.candX[1], w.candU[0], w.candU[1], w.slot,
                                                w.parity, w.Jlast, w.Jstar, X, U, J, J_star);
     DPILQR_CUDA(cudaGetLastError());
+    if (stream != user_stream) {  // whatever the caller enqueues next on its own stream comes after the tail
+        DPILQR_CUDA(cudaEventRecord(ctx->ev, stream));
+        DPILQR_CUDA(cudaStreamWaitEvent(user_stream, ctx->ev, 0));
+    }
     DPILQR_CUDA(cudaStreamSynchronize(stream));
     timer.flush();
     return total_iters;
 }
 
 // ---- cached device memory for the host-buffer entry point --------------------------------------
-struct HostCache {
-    std::mutex lock;
+// A small pool of arenas, one per call in flight (host threads may call concurrently, see BulkGate).
+struct HostArena {
     int device = -1;
     void *buf = nullptr;
     int64_t bytes = 0;
+    bool in_use = false;
+};
+constexpr int kMaxArenas = 4;
+struct HostCache {
+    std::mutex lock;
+    std::condition_variable cv;
+    HostArena arena[kMaxArenas];
 };
 static HostCache g_cache;
+
+// Borrow an arena of at least `bytes` on `device`: a free one that fits, else a free one re-allocated, else wait.
+static int arena_acquire(int device, int64_t bytes, HostArena **out)
+{
+    std::unique_lock<std::mutex> lk(g_cache.lock);
+    for (;;) {
+        HostArena *pick = nullptr;
+        for (auto &ar : g_cache.arena)
+            if (!ar.in_use && ar.device == device && ar.bytes >= bytes && (!pick || ar.bytes < pick->bytes)) pick = &ar;
+        if (!pick)
+            for (auto &ar : g_cache.arena)
+                if (!ar.in_use && !ar.buf) { pick = &ar; break; }
+        if (!pick)
+            for (auto &ar : g_cache.arena)
+                if (!ar.in_use) { pick = &ar; break; }
+        if (pick) {
+            if (pick->device != device || pick->bytes < bytes) {
+                if (pick->buf) { cudaSetDevice(pick->device); cudaFree(pick->buf); cudaSetDevice(device); }
+                pick->buf = nullptr; pick->bytes = 0; pick->device = device;
+                DPILQR_CUDA(cudaMalloc(&pick->buf, bytes));
+                pick->bytes = bytes;
+            }
+            pick->in_use = true;
+            *out = pick;
+            return DPILQR_OK;
+        }
+        g_cache.cv.wait(lk);
+    }
+}
+
+struct ArenaLease {
+    HostArena *arena = nullptr;
+    ~ArenaLease()
+    {
+        if (!arena) return;
+        {
+            std::lock_guard<std::mutex> lk(g_cache.lock);
+            arena->in_use = false;
+        }
+        g_cache.cv.notify_one();
+    }
+};
 
 }  // namespace dpilqr
 
@@ -649,15 +788,12 @@ int64_t dpilqr_solve_batch_host(const dpilqr_batch *hb, const dpilqr_solve_opts 
     const int64_t ws_bytes = dpilqr_workspace_bytes(B, a, s, c, T, NA);
     const int64_t o_ws = reserve(ws_bytes);
 
-    std::lock_guard<std::mutex> guard(g_cache.lock);
-    if (g_cache.device != device || g_cache.bytes < off) {
-        if (g_cache.buf) { cudaSetDevice(g_cache.device); cudaFree(g_cache.buf); cudaSetDevice(device); }
-        g_cache.buf = nullptr; g_cache.bytes = 0; g_cache.device = device;
-        DPILQR_CUDA(cudaMalloc(&g_cache.buf, off));
-        g_cache.bytes = off;
-    }
-    char *base = (char *)g_cache.buf;
-    cudaStream_t stream = 0;
+    ArenaLease lease;
+    if ((rc = arena_acquire(device, off, &lease.arena))) return rc;
+    char *base = (char *)lease.arena->buf;
+    ThreadContext *ctx = nullptr;
+    if ((rc = thread_context(&ctx))) return rc;
+    cudaStream_t stream = ctx->host;  // one stream per calling thread: concurrent callers overlap
     auto h2d = [&](int64_t o, const void *src, int64_t bytes) -> int {
         if (!src || bytes == 0) return 0;
         return check_cuda(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, stream), "H2D");
@@ -729,13 +865,14 @@ int dpilqr_debug_backward_timing(long long *device_counters)
 int dpilqr_release_cache(void)
 {
     std::lock_guard<std::mutex> guard(g_cache.lock);
-    if (g_cache.buf) {
-        cudaSetDevice(g_cache.device);
-        cudaFree(g_cache.buf);
+    for (auto &ar : g_cache.arena) {
+        if (ar.in_use || !ar.buf) continue;
+        cudaSetDevice(ar.device);
+        cudaFree(ar.buf);
+        ar.buf = nullptr;
+        ar.bytes = 0;
+        ar.device = -1;
     }
-    g_cache.buf = nullptr;
-    g_cache.bytes = 0;
-    g_cache.device = -1;
     return 0;
 }
 

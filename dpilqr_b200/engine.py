@@ -387,3 +387,63 @@ def solve_specs(specs, x0s, U0s, N, device=None, on_error="raise", **kw):
         for res in results:
             raise_for_status(res["status"])
     return results
+
+
+class SolvePipeline:
+    """Keeps ``depth`` batched solves in flight on one device (not in the reference, whose batches are a process pool).
+
+    One worker thread and one CUDA stream per solve in flight.  The library makes concurrent callers take turns for the
+    bulk of a solve -- the launches that fill the machine -- and runs the tail of a solve (the few problems that need many
+    more iterations than the rest: a tenth of the time of a 4096-scenario batch for 1.5 % of its work) on a
+    high-priority stream beside the next solve's bulk (csrc/solver.cu, BulkGate).  Throughput of a stream of batches
+    then follows their work rather than the latency of their stragglers.
+
+        pipe = SolvePipeline(device, depth=2)
+        for out in pipe.map(lambda args: batch.solve(*args), jobs): ...
+    """
+
+    def __init__(self, device=None, depth=2):
+        from concurrent.futures import ThreadPoolExecutor
+
+        _native.require_device()
+        self.device = torch.device(device) if device is not None else default_device()
+        self.depth = max(1, int(depth))
+        self._pool = ThreadPoolExecutor(max_workers=self.depth, thread_name_prefix="dpilqr-solve")
+        self._streams = {}
+
+    def _run(self, fn, item):
+        import threading
+
+        torch.cuda.set_device(self.device)
+        key = threading.get_ident()
+        stream = self._streams.get(key)
+        if stream is None:
+            stream = self._streams[key] = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(stream):
+            out = fn(item)
+            stream.synchronize()
+        return out
+
+    def submit(self, fn, item):
+        return self._pool.submit(self._run, fn, item)
+
+    def map(self, fn, items):
+        """Results in submission order; at most ``depth`` items are in flight."""
+        from collections import deque
+
+        pending = deque()
+        for item in items:
+            if len(pending) >= self.depth:
+                yield pending.popleft().result()
+            pending.append(self.submit(fn, item))
+        while pending:
+            yield pending.popleft().result()
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
