@@ -842,17 +842,84 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 }
             }
         } else {
-            for (int col = tid; col <= n; col += nthr) {  // runtime sizes: one thread per right-hand side
-                double *xcol = KB + col;
-                for (int k = 0; k < m; ++k) xcol[(size_t)k * LDN] = -QUX[(size_t)order[k] * LDN + col];
-                for (int k = 0; k < m - 1; ++k) {
-                    const double xk = xcol[(size_t)k * LDN];
-                    for (int k2 = k + 1; k2 < m; ++k2) xcol[(size_t)k2 * LDN] = fma(-Lp[k * LDF + k2], xk, xcol[(size_t)k2 * LDN]);
+            // runtime sizes: one thread per right-hand side, blocked by eight rows.  The eight unknowns of a block are
+            // solved in registers; the rows outside the block are updated four at a time with every load of a batch
+            // issued before its first use -- the column lives in shared memory or, for large teams, in the L2 scratch,
+            // and an update chained one load-FMA-store after the other costs a full round trip per entry (2 M cycles
+            // per time step for 15 drones).
+            for (int col = tid; col <= n; col += nthr) {
+                double *__restrict__ xcol = KB + col;
+                const double *__restrict__ lp = Lp;
+                const double *__restrict__ up = Up;
+                for (int k0 = 0; k0 < m; k0 += 8) {
+                    double xv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) xv[e] = (k0 + e < m) ? -QUX[(size_t)order[k0 + e] * LDN + col] : 0.0;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (k0 + e < m) xcol[(size_t)(k0 + e) * LDN] = xv[e];
                 }
-                for (int cc = m - 1; cc >= 0; --cc) {
-                    const double xc = xcol[(size_t)cc * LDN] * rdiag[cc];
-                    xcol[(size_t)cc * LDN] = xc;
-                    for (int k = 0; k < cc; ++k) xcol[(size_t)k * LDN] = fma(-Up[cc * LDF + k], xc, xcol[(size_t)k * LDN]);
+                // ---- forward: unit lower factor, lp[k * LDF + k2] = l(k2, k), k2 > k
+                for (int k0 = 0; k0 < m; k0 += 8) {
+                    double x[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = (k0 + e < m) ? xcol[(size_t)(k0 + e) * LDN] : 0.0;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+#pragma unroll
+                        for (int f = e + 1; f < 8; ++f)
+                            if (k0 + f < m) x[f] = fma(-lp[(k0 + e) * LDF + k0 + f], x[e], x[f]);
+#pragma unroll
+                    for (int e = 1; e < 8; ++e)
+                        if (k0 + e < m) xcol[(size_t)(k0 + e) * LDN] = x[e];
+                    for (int k2 = k0 + 8; k2 < m; k2 += 4) {
+                        double v[4], l[4][8];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int row = min(k2 + r, m - 1);
+                            v[r] = xcol[(size_t)row * LDN];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) l[r][e] = lp[(k0 + e) * LDF + row];
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[r] = fma(-l[r][e], x[e], v[r]);
+                            if (k2 + r < m) xcol[(size_t)(k2 + r) * LDN] = v[r];
+                        }
+                    }
+                }
+                // ---- backward: upper factor, up[c * LDF + k] = u(k, c), k <= c
+                for (int k0 = ((m - 1) >> 3) << 3; k0 >= 0; k0 -= 8) {
+                    double x[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = (k0 + e < m) ? xcol[(size_t)(k0 + e) * LDN] : 0.0;
+#pragma unroll
+                    for (int e = 7; e >= 0; --e) {
+                        if (k0 + e < m) {
+                            x[e] *= rdiag[k0 + e];
+#pragma unroll
+                            for (int f = 0; f < e; ++f) x[f] = fma(-up[(k0 + e) * LDF + k0 + f], x[e], x[f]);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (k0 + e < m) xcol[(size_t)(k0 + e) * LDN] = x[e];
+                    for (int k2 = 0; k2 < k0; k2 += 4) {  // k0 is a multiple of 8: whole batches of four rows
+                        double v[4], uu[4][8];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            v[r] = xcol[(size_t)(k2 + r) * LDN];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) uu[r][e] = (k0 + e < m) ? up[(k0 + e) * LDF + k2 + r] : 0.0;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[r] = fma(-uu[r][e], x[e], v[r]);
+                            xcol[(size_t)(k2 + r) * LDN] = v[r];
+                        }
+                    }
                 }
             }
         }
@@ -1145,10 +1212,18 @@ int launch_backward(const BackwardParams &p_in, int n_blocks, cudaStream_t strea
         return DPILQR_E_INVALID;
     }
     if (s == 12 && c == 4) {
+        // tensor-path instantiations: even team sizes (an 8-row tile of the control rows is two agents); 12 and 14
+        // agents keep Q_ux, K and the LU factors in the L2-resident scratch
         static const bool force_generic = getenv("DPILQR_BACKWARD_FORCE_GENERIC") != nullptr;  // experiments / cross-checks
-        if (a == 10 && !plan.use_global_scratch && !force_generic) {
-            if (p.timing != nullptr) return launch_typed<12, 4, 10, false, true>(p, n_blocks, plan, stream);
-            return launch_typed<12, 4, 10, false>(p, n_blocks, plan, stream);
+        if (!force_generic) {
+            if (a == 10 && !plan.use_global_scratch) {
+                if (p.timing != nullptr) return launch_typed<12, 4, 10, false, true>(p, n_blocks, plan, stream);
+                return launch_typed<12, 4, 10, false>(p, n_blocks, plan, stream);
+            }
+            if (a == 6 && !plan.use_global_scratch) return launch_typed<12, 4, 6, false>(p, n_blocks, plan, stream);
+            if (a == 8 && !plan.use_global_scratch) return launch_typed<12, 4, 8, false>(p, n_blocks, plan, stream);
+            if (a == 12 && plan.use_global_scratch) return launch_typed<12, 4, 12, true>(p, n_blocks, plan, stream);
+            if (a == 14 && plan.use_global_scratch) return launch_typed<12, 4, 14, true>(p, n_blocks, plan, stream);
         }
         return launch_generic<12, 4>(p, n_blocks, plan, stream);
     }

@@ -56,6 +56,7 @@ struct LinQuadParams {
     const int32_t *active;
     const int32_t *n_active;
     int n_blocks_per_problem;
+    int records_per_cta;  // consecutive stage records a CTA builds in shared memory and stores in one bulk copy
 };
 
 struct BackwardParams {

@@ -124,8 +124,11 @@ __device__ __noinline__ void lu_lookahead(double *__restrict__ W, double *__rest
         return;
     }
     // ---------------------------------------------------------------------- row threads
-    const int r = gt / tpr, q = gt - r * tpr;
-    const bool myrow = r < m;
+    // A row's threads synchronise with __syncwarp(): rows never straddle a warp (with three threads per row a warp
+    // takes ten rows and its last two lanes idle)
+    const int rows_per_warp = 32 / tpr;
+    const int r = (gt >> 5) * rows_per_warp + lane / tpr, q = lane % tpr;
+    const bool myrow = r < m && lane < rows_per_warp * tpr;
     double *wrow = W + (myrow ? r : m - 1) * ldw;
     bool mydone = !myrow;
     double2 wreg[NP];  // this thread's column pairs of row r

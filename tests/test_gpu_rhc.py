@@ -91,11 +91,12 @@ def test_single_agent_reference_cost_problem():
     assert rel_err(X, Xo) < 1e-8 and rel_err(U, Uo) < 1e-8 and abs(J - Jo) <= 1e-8 * abs(Jo)
 
 
-@pytest.mark.parametrize("a,seed", [(1, 3), (2, 3), (7, 3), (12, 5), (15, 3)])
+@pytest.mark.parametrize("a,seed", [(1, 3), (2, 3), (3, 1), (4, 3), (5, 2), (6, 3), (7, 3), (8, 3), (12, 5), (14, 5), (15, 3)])
 def test_backward_pass_all_sizes_vs_oracle(a, seed):
-    """Every code path of the backward kernel (tensor path for even agent counts with compile-time sizes, generic
-    DFMA path, and the L2-scratch path for teams too large for shared memory) against the oracle's
-    _backward_pass on the hover rollout of a random Quadcopter12D scenario."""
+    """Every code path of the backward kernel (small-problem kernels for up to five drones, tensor path with
+    compile-time sizes for 6, 8, 10 drones and -- on the L2 scratch -- 12 and 14, generic DFMA path, generic L2-scratch
+    path) against the oracle's _backward_pass on the hover rollout of a random Quadcopter12D scenario and on the
+    iterate after one iLQR iteration (tilted drones, active proximity terms)."""
     import dpilqr_b200 as dp
     from dpilqr_b200 import scenarios
     from oracle import ilqr_oracle as O
@@ -122,6 +123,13 @@ def test_backward_pass_all_sizes_vs_oracle(a, seed):
     Xs, Us, Js = solver.solve(x0, U0.copy(), n_lqr_iter=1)
     assert int(out["trace_alpha"][0, 0]) == solver.trace[0]["alpha_index"]
     assert rel_err(out["X"][0].cpu().numpy(), Xs) < TOL and rel_err(out["U"][0].cpu().numpy(), Us) < TOL
+    if solver.trace[0]["alpha_index"] >= 0:  # the backward pass of the second iteration, from the oracle's iterate
+        stage, _ = batch.linearize_quadraticize(Xs[None], Us[None])
+        K, d, st = batch.backward(stage, solver.mu)
+        K2, d2 = solver.backward_pass(Xs, Us)
+        eK, ed = rel_err(K[0].cpu().numpy(), K2), rel_err(d[0].cpu().numpy(), d2)
+        print(f"a={a}: second-iterate gains K err {eK:.1e} d err {ed:.1e}")
+        assert eK < TOL and ed < TOL
 
 
 # --------------------------------------------------------------------------------------------
