@@ -1179,6 +1179,12 @@ static int launch_typed(const BackwardParams &p, int n_blocks, const BackwardPla
 template <int S, int C>
 static int launch_generic(const BackwardParams &p, int n_blocks, const BackwardPlan &plan, cudaStream_t stream)
 {
+    if constexpr (S == 12 && C == 4) {  // instrumented builds of the generic paths (tools/backward_phases.py)
+        if (p.timing != nullptr) {
+            if (plan.use_global_scratch) return launch_typed<S, C, 0, true, true>(p, n_blocks, plan, stream);
+            return launch_typed<S, C, 0, false, true>(p, n_blocks, plan, stream);
+        }
+    }
     if (plan.use_global_scratch) return launch_typed<S, C, 0, true>(p, n_blocks, plan, stream);
     return launch_typed<S, C, 0, false>(p, n_blocks, plan, stream);
 }

@@ -10,6 +10,8 @@
 //   GameCost.quadraticize                                reference cost.py:208-239
 // The proximity terms of agent i are accumulated over the other agents in ascending order,
 // which is the order in which the reference's pair loop touches agent i's entries.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace dpilqr {
@@ -44,16 +46,34 @@ __device__ __forceinline__ bool pair_quadratic(const double *pa, const double *p
     return true;
 }
 
-// A CTA builds a GROUP of consecutive stage records of one problem (p.records_per_cta of them: as many as 64 kB of
-// shared memory and 128 threads hold) in shared memory and streams the group out with one TMA bulk store: records of a
-// problem are contiguous in HBM, so the store is a single fully coalesced run of up to 64 kB.  (The first version wrote
-// every agent's 146-double Jacobian block straight from its thread: neighbouring threads 1168 bytes apart, every
-// store instruction 32 sectors -- 0.21 of the HBM roofline.)
-//   1  all threads lay the identity / zero background of the group (16-byte shared-memory stores)
-//   2  one thread per (record, agent) computes its slice -- proximity terms, cost gradients, Jacobian non-zeros --
-//      on top of it
+// A CTA builds a GROUP of consecutive stage records of one problem (p.records_per_cta of them) in shared memory and
+// streams the group out with TMA bulk stores: records of a problem are contiguous in HBM, so the group leaves as one
+// fully coalesced run of up to 63 kB.  (The first version wrote every agent's 146-double Jacobian block straight from
+// its thread: neighbouring threads 1168 bytes apart, every store instruction 32 sectors -- 0.21 of the HBM roofline.)
+//   1  all threads lay the zero background of the group (16-byte shared-memory stores)
+//   2a the unit diagonals of the A blocks; one thread per (record, agent pair) evaluates the pair's penalty gradient /
+//      Hessian once, into a table; the off-diagonal Hessian block of the pair goes straight into the record
+//   2b one thread per (record, agent): proximity sums, cost gradients, Jacobian non-zeros on top of the background
 //   3  fence to the async proxy, one thread issues cp.async.bulk shared -> global and waits for the read side
-__global__ void __launch_bounds__(128) linquad_kernel(const LinQuadParams p)
+constexpr int kLinquadThreads = 128;
+
+struct LinquadSmem {
+    int recs, ptab, total_doubles;
+};
+
+__host__ __device__ inline LinquadSmem linquad_smem(int a, int s, int c, int rpc)
+{
+    const StageLayout L = stage_layout(a, s, c);
+    auto even = [](int v) { return (v + 1) & ~1; };
+    LinquadSmem M{};
+    int off = 0;
+    M.recs = off; off += rpc * L.stride;
+    M.ptab = off; off += even(rpc * L.pairs * 10);  // [rec][pair]: inside flag, g[3], H[6]
+    M.total_doubles = off;
+    return M;
+}
+
+__global__ void __launch_bounds__(kLinquadThreads) linquad_kernel(const LinQuadParams p)
 {
     extern __shared__ __align__(16) double lq_smem[];
     const Batch &bt = p.batch;
@@ -66,73 +86,56 @@ __global__ void __launch_bounds__(128) linquad_kernel(const LinQuadParams p)
     const int t0 = (blockIdx.x % p.n_blocks_per_problem) * RPC;
     const int nrec = min(RPC, T + 1 - t0);
     const StageLayout L = stage_layout(a, s, c);
+    const LinquadSmem SM = linquad_smem(a, s, c, RPC);
     const int tid = threadIdx.x, nthr = blockDim.x;
+    const int pairs = L.pairs;
+    double *ptab = lq_smem + SM.ptab;
+    const int slot = p.slot ? p.slot[b] : 0;
+    const double *xbase = p.X + (int64_t)b * p.x_stride + (int64_t)slot * p.x_slot_stride + (int64_t)t0 * n;
+    const double *ubase = p.U + (int64_t)b * p.u_stride + (int64_t)slot * p.u_slot_stride + (int64_t)t0 * m;
+    const double *xf = bt.xf + (int64_t)b * n;
 
-    // ---- 1: background of every record of the group: A_i = I, everything else zero
+    // ---- 1: zero background
     {
         const int total2 = nrec * L.stride / 2;  // the stride is even
-        const int ss = s * s;
-        for (int e = tid; e < total2; e += nthr) {
-            const int off = (2 * e) % L.stride;
-            double v0 = 0.0, v1 = 0.0;
-            if (off < L.offB) {
-                const int r0 = off % L.strideA, r1 = r0 + 1;  // strideA is even iff s*s is: a pair never straddles two blocks then
-                v0 = (r0 < ss && r0 / s == r0 % s) ? 1.0 : 0.0;
-                v1 = (r1 < ss && r1 / s == r1 % s) ? 1.0 : 0.0;
-                if ((L.strideA & 1) != 0) {  // odd block stride: locate both entries on their own
-                    const int q1 = (off + 1) % L.strideA;
-                    v1 = (off + 1 < L.offB && q1 < ss && q1 / s == q1 % s) ? 1.0 : 0.0;
-                }
-            }
-            *reinterpret_cast<double2 *>(lq_smem + 2 * e) = make_double2(v0, v1);
-        }
+        const double2 zero2 = make_double2(0.0, 0.0);
+        for (int e = tid; e < total2; e += nthr) reinterpret_cast<double2 *>(lq_smem)[e] = zero2;
     }
     __syncthreads();
 
-    // ---- 2: one thread per (record, agent)
+    // ---- 2a: A_i = I; one thread per (record, agent pair)
+    for (int k = tid; k < nrec * n; k += nthr) {
+        const int tl = k / n, row = k - tl * n;
+        const int i = row / s, r = row - i * s;
+        lq_smem[(size_t)tl * L.stride + L.offA + i * L.strideA + r * s + r] = 1.0;
+    }
     int st = 0;
-    if (tid < nrec * a) {
-    const int tl = tid / a, i = tid - tl * a;
-    const int t = t0 + tl;
-    const bool terminal = (t == T);
-    const int slot = p.slot ? p.slot[b] : 0;
-    const double *xt = p.X + (int64_t)b * p.x_stride + (int64_t)slot * p.x_slot_stride + (int64_t)t * n;
-    const double *ut = terminal ? nullptr
-                                : p.U + (int64_t)b * p.u_stride + (int64_t)slot * p.u_slot_stride + (int64_t)t * m;
-    double *rec = lq_smem + (size_t)tl * L.stride;
-
-    const int32_t *ndims_b = bt.n_dims + (int64_t)b * a;
-    const int model = bt.model[(int64_t)b * a + i];
-    const int ci = bt.cost_idx[(int64_t)b * a + i];
     const bool has_prox = (a > 1) && (bt.has_prox == nullptr || bt.has_prox[b] != 0);
-    const double w_ref = bt.weights ? bt.weights[2 * b] : 1.0;
     const double w_prox = bt.weights ? bt.weights[2 * b + 1] : 200.0;
-
-    // ---- proximity terms of agent i (position = first coordinates of each agent's state)
-    double gsum[3] = {0.0, 0.0, 0.0};
-    double hsum[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double w_ref = bt.weights ? bt.weights[2 * b] : 1.0;
     if (has_prox) {
         const double radius = bt.radius[b];
-        const int nd_i = ndims_b[i];
-        for (int j = 0; j < a; ++j) {
-            if (j == i) continue;
-            const int lo = i < j ? i : j, hi = i < j ? j : i;
-            const int nd = min(nd_i, ndims_b[j]);
+        const int32_t *ndims_b = bt.n_dims + (int64_t)b * a;
+        for (int item = tid; item < nrec * pairs; item += nthr) {
+            const int tl = item / pairs, pr = item - tl * pairs;
+            int i = 0, rem = pr;
+            while (rem >= a - 1 - i) { rem -= a - 1 - i; ++i; }
+            const int j = i + 1 + rem;
+            const double *xt = xbase + (size_t)tl * n;
+            const int nd = min(ndims_b[i], ndims_b[j]);
             double g[3] = {0.0, 0.0, 0.0}, H[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             bool mismatch;
-            const bool inside = pair_quadratic(xt + lo * s, xt + hi * s, nd, radius, g, H, mismatch);
+            const bool inside = pair_quadratic(xt + i * s, xt + j * s, nd, radius, g, H, mismatch);
             if (mismatch) st |= DPILQR_ST_POINT_NDIM;
             if (nd < 3) { g[2] = 0.0; H[2] = 0.0; H[4] = 0.0; H[5] = 0.0; }
-            const double sign = (i == lo) ? 1.0 : -1.0;
-            // the reference adds a (zero) pair contribution even when outside the radius
-            if (inside) {
+            double *row = ptab + (size_t)item * 10;
+            row[0] = inside ? 1.0 : 0.0;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) gsum[k] += sign * g[k];
+            for (int k = 0; k < 3; ++k) row[1 + k] = g[k];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) hsum[k] += H[k];
-            }
-            if (j > i && inside) {  // off-diagonal block of pair (i, j); zero (the background) outside the radius
-                double *Ho = rec + L.offHo + 9 * pair_index(i, j, a);
+            for (int k = 0; k < 6; ++k) row[4 + k] = H[k];
+            if (inside) {  // off-diagonal block of pair (i, j); zero (the background) outside the radius
+                double *Ho = lq_smem + (size_t)tl * L.stride + L.offHo + 9 * pr;
                 const double h[6] = {-w_prox * H[0], -w_prox * H[1], -w_prox * H[2], -w_prox * H[3], -w_prox * H[4], -w_prox * H[5]};
                 Ho[0] = h[0]; Ho[1] = h[1]; Ho[2] = h[2];
                 Ho[3] = h[1]; Ho[4] = h[3]; Ho[5] = h[4];
@@ -140,60 +143,88 @@ __global__ void __launch_bounds__(128) linquad_kernel(const LinQuadParams p)
             }
         }
     }
-    {
+    __syncthreads();
+
+    // ---- 2b: one thread per (record, agent): proximity sums, cost gradients, Jacobian non-zeros
+    if (tid < nrec * a) {
+        const int tl = tid / a, i = tid - tl * a;
+        const bool terminal = (t0 + tl == T);
+        double *rec = lq_smem + (size_t)tl * L.stride;
+        double gsum[3] = {0.0, 0.0, 0.0};
+        double hsum[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (has_prox) {  // the pairs of agent i, the other agent ascending (the order of the reference's pair loop)
+            for (int j = 0; j < a; ++j) {
+                if (j == i) continue;
+                const int lo = i < j ? i : j, hi = i < j ? j : i;
+                const double *row = ptab + ((size_t)tl * pairs + pair_index(lo, hi, a)) * 10;
+                const double sign = (i == lo) ? 1.0 : -1.0;
+                if (row[0] != 0.0) {  // the reference adds a (zero) pair contribution even when outside the radius
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) gsum[k] += sign * row[1 + k];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) hsum[k] += row[4 + k];
+                }
+            }
+        }
         double *Hd = rec + L.offHd + 9 * i;
         Hd[0] = w_prox * hsum[0]; Hd[1] = w_prox * hsum[1]; Hd[2] = w_prox * hsum[2];
         Hd[3] = w_prox * hsum[1]; Hd[4] = w_prox * hsum[3]; Hd[5] = w_prox * hsum[4];
         Hd[6] = w_prox * hsum[2]; Hd[7] = w_prox * hsum[4]; Hd[8] = w_prox * hsum[5];
-    }
-
-    // ---- reference-cost gradients and dynamics Jacobians
-    dispatch_model(model, [&]<int M>() {
-        constexpr int NX = model_nx(M), NU = model_nu(M);
-        double x[NX], u[NU], e[NX];
+        const double *xt = xbase + (size_t)tl * n + i * s;
+        const double *et = xf + i * s;
+        const double *ut = ubase + (size_t)tl * m + i * c;  // (not read for the terminal record)
+        const int64_t ci = bt.cost_idx[(int64_t)b * a + i];
+        dispatch_model(bt.model[(int64_t)b * a + i], [&]<int M>() {
+            constexpr int NX = model_nx(M), NU = model_nu(M);
+            double x[NX], u[NU], e[NX];
 #pragma unroll
-        for (int k = 0; k < NX; ++k) { x[k] = xt[i * s + k]; e[k] = x[k] - bt.xf[(int64_t)b * n + i * s + k]; }
+            for (int k = 0; k < NX; ++k) { x[k] = xt[k]; e[k] = x[k] - et[k]; }
 #pragma unroll
-        for (int k = 0; k < NU; ++k) u[k] = terminal ? 0.0 : ut[i * c + k];
-        const double *Qm = (terminal ? bt.Qf : bt.Q) + (int64_t)ci * NX * NX;
-        const double *Rm = bt.R + (int64_t)ci * NU * NU;
-        double *Lx = rec + L.offLx + i * s;
-        double *Lu = rec + L.offLu + i * c;
+            for (int k = 0; k < NU; ++k) u[k] = terminal ? 0.0 : ut[k];
+            const double *Qm = (terminal ? bt.Qf : bt.Q) + ci * NX * NX;
+            const double *Rm = bt.R + ci * NU * NU;
+            double *Lx = rec + L.offLx + i * s;
+            double *Lu = rec + L.offLu + i * c;
 #pragma unroll
-        for (int j = 0; j < NX; ++j) {
-            double v = 0.0;
+            for (int j = 0; j < NX; ++j) {
+                double v = 0.0;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) v += e[k] * (Qm[k * NX + j] + Qm[j * NX + k]);
-            double lx = w_ref * v;
-            if (has_prox && j < 3) lx += w_prox * gsum[j];
-            if (!isfinite(lx)) st |= DPILQR_ST_NONFINITE;
-            Lx[j] = lx;
-        }
-#pragma unroll
-        for (int j = 0; j < NU; ++j) {
-            double v = 0.0;
-            if (!terminal) {
-#pragma unroll
-                for (int k = 0; k < NU; ++k) v += u[k] * (Rm[k * NU + j] + Rm[j * NU + k]);
+                for (int k = 0; k < NX; ++k) v += e[k] * (Qm[k * NX + j] + Qm[j * NX + k]);
+                double lx = w_ref * v;
+                if (has_prox && j < 3) lx += w_prox * gsum[j];
+                if (!isfinite(lx)) st |= DPILQR_ST_NONFINITE;
+                Lx[j] = lx;
             }
-            Lu[j] = w_ref * v;
-        }
-        if (!terminal) {
-            EulerDenseSink sink{rec + L.offA + i * L.strideA, rec + L.offB + i * L.strideB, NX, NU, bt.dt};
-            model_jacobian<M>(x, u, sink);
-        }
-    });
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+                double v = 0.0;
+                if (!terminal) {
+#pragma unroll
+                    for (int k = 0; k < NU; ++k) v += u[k] * (Rm[k * NU + j] + Rm[j * NU + k]);
+                }
+                Lu[j] = w_ref * v;
+            }
+            if (!terminal) {
+                EulerDenseSink sink{rec + L.offA + i * L.strideA, rec + L.offB + i * L.strideB, NX, NU, bt.dt};
+                model_jacobian<M>(x, u, sink);
+            }
+        });
     }
     if (st != 0 && p.status) atomicOr(p.status + b, st);
 
-    // ---- 3: the group leaves in one bulk store
+    // ---- 3: the group leaves in bulk stores
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
         double *dst = p.stage + ((int64_t)b * (T + 1) + t0) * L.stride;
         const unsigned bytes = (unsigned)(nrec * L.stride * 8);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                     "r"((unsigned)__cvta_generic_to_shared(lq_smem)), "r"(bytes) : "memory");
+        // several medium-sized copies move faster than one large one: they are processed concurrently
+        constexpr unsigned kChunk = 4096;
+        const unsigned src = (unsigned)__cvta_generic_to_shared(lq_smem);
+#pragma unroll 1
+        for (unsigned off = 0; off < bytes; off += kChunk)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<char *>(dst) + off),
+                         "r"(src + off), "r"(min(kChunk, bytes - off)) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be released once it has been read
     }
@@ -204,15 +235,19 @@ int launch_linquad(const LinQuadParams &p_in, int n_problems, cudaStream_t strea
     if (n_problems <= 0) return DPILQR_OK;
     LinQuadParams p = p_in;
     const Batch &bt = p.batch;
-    const StageLayout L = stage_layout(bt.n_agents, bt.s, bt.c);
-    const int threads = 128;
-    const size_t rec_bytes = (size_t)L.stride * 8;
-    if (rec_bytes > 200 * 1024 || bt.n_agents > threads) {
-        set_error("linearise/quadraticise kernel: a stage record of %d agents does not fit shared memory", bt.n_agents);
+    const int a = bt.n_agents, s = bt.s, c = bt.c;
+    static const int env_threads = getenv("DPILQR_LQ_THREADS") ? atoi(getenv("DPILQR_LQ_THREADS")) : 0;
+    static const int env_kb = getenv("DPILQR_LQ_KB") ? atoi(getenv("DPILQR_LQ_KB")) : 0;
+    const int threads = env_threads ? env_threads : kLinquadThreads;
+    const size_t one = (size_t)linquad_smem(a, s, c, 1).total_doubles * 8;
+    if (one > 200 * 1024 || a > threads) {
+        set_error("linearise/quadraticise kernel: a stage record of %d agents does not fit shared memory", a);
         return DPILQR_E_UNSUPPORTED;
     }
-    int rpc = (int)((64 * 1024) / rec_bytes);
-    if (rpc > threads / bt.n_agents) rpc = threads / bt.n_agents;
+    // records per CTA: three CTAs of up to 74 kB per SM (measured: 1.56 ms for 4096 ten-drone problems against 1.9 to
+    // 2.7 ms with one, two or four records per CTA, with 64 or 256 threads, or with the inputs staged in shared memory)
+    int rpc = (int)(((env_kb ? env_kb : 74) * 1024) / one);
+    if (rpc > threads / a) rpc = threads / a;
     if (rpc > bt.horizon + 1) rpc = bt.horizon + 1;
     if (rpc < 1) rpc = 1;
     // groups of equal size: the last CTA of a problem does not run nearly empty
@@ -220,7 +255,7 @@ int launch_linquad(const LinQuadParams &p_in, int n_problems, cudaStream_t strea
     rpc = (bt.horizon + 1 + groups - 1) / groups;
     p.records_per_cta = rpc;
     p.n_blocks_per_problem = groups;
-    const size_t smem = rpc * rec_bytes;
+    const size_t smem = (size_t)linquad_smem(a, s, c, rpc).total_doubles * 8;
     if (smem > 48 * 1024) DPILQR_CUDA(cudaFuncSetAttribute(linquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     linquad_kernel<<<n_problems * p.n_blocks_per_problem, threads, smem, stream>>>(p);
     DPILQR_CUDA(cudaGetLastError());
