@@ -1202,6 +1202,9 @@ int launch_backward(const BackwardParams &p_in, int n_blocks, cudaStream_t strea
     const int a = bt.n_agents, s = bt.s, c = bt.c;
     // small problems (DP-iLQR neighbourhoods, small teams): several problems per SM (backward_small.cu)
     static const bool force_big = getenv("DPILQR_BACKWARD_FORCE_BIG") != nullptr;  // experiments / cross-checks
+    static const bool no_warp = getenv("DPILQR_BACKWARD_NO_WARP") != nullptr;            // experiments / cross-checks
+    // tiny problems (one or two drones, up to eight planar agents): one warp per problem (backward_warp.cu)
+    if (!force_big && !no_warp && p.timing == nullptr && backward_warp_applies(a, s, c)) return launch_backward_warp(p, n_blocks, stream);
     if (!force_big && p.timing == nullptr && backward_small_applies(a, s, c)) return launch_backward_small(p, n_blocks, stream);
     if (a * c > 64) {
         set_error("backward kernel: at most 64 joint controls are supported (got %d)", a * c);

@@ -69,6 +69,7 @@ struct BackwardParams {
     const int32_t *active;
     const int32_t *n_active;
     double *scratch;  // global scratch for the big-problem path (2*m*n doubles per CTA)
+    int n_launch;     // problems of this launch (kernels whose grid is rounded up to whole CTAs of several problems)
     int use_global_scratch;
     long long *timing;  // optional: 20 per-phase cycle counters written by CTA 0 (debug aid)
     int debug_mode;     // timing experiments of the instrumented build only (wrong numerics), env DPILQR_DEBUG_BACKWARD_MODE:
@@ -82,7 +83,9 @@ int launch_linquad(const LinQuadParams &p, int n_problems, cudaStream_t stream);
 int launch_stage_to_dense(const Batch &bt, const double *stage, double *A, double *Bm, double *Lx, double *Lu,
                           double *Lxx, double *Luu, cudaStream_t stream);
 int launch_backward(const BackwardParams &p, int n_blocks, cudaStream_t stream);
-bool backward_small_applies(int a, int s, int c);  // backward_small.cu: n <= 64, m <= 32
+bool backward_small_applies(int a, int s, int c);
+bool backward_warp_applies(int a, int s, int c);  // tiny problems: one warp per problem (backward_warp.cu)
+int launch_backward_warp(const BackwardParams &p, int n_blocks, cudaStream_t stream);  // backward_small.cu: n <= 64, m <= 32
 int launch_backward_small(const BackwardParams &p, int n_blocks, cudaStream_t stream);
 int64_t backward_scratch_doubles(int n_problems, int a, int s, int c);
 int launch_inter_graph(const double *X, int64_t n_scen, int rows, int a, int s, const double *radius, uint64_t *adj,
