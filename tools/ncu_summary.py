@@ -37,8 +37,14 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def raw():
+    """stdin: `ncu -i X.ncu-rep --page raw --csv`; argv[2] (optional): substring of the kernel name, argv[3]: which match"""
     rows = list(csv.reader(sys.stdin))
-    hdr, unit, vals = rows[0], rows[1], rows[-1]
+    hdr, unit = rows[0], rows[1]
+    body = rows[2:]
+    if len(sys.argv) > 2 and "Kernel Name" in hdr:
+        kn = hdr.index("Kernel Name")
+        body = [r for r in body if len(r) > kn and sys.argv[2] in r[kn]]
+    vals = body[int(sys.argv[3]) if len(sys.argv) > 3 else -1]
     print("kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?")
     for i, h in enumerate(hdr):
         if h in WANT or h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio"):
