@@ -61,18 +61,19 @@ __host__ __device__ constexpr size_t even_up(size_t v) { return (v + 1) & ~(size
 // doubles of global (L2-resident) scratch per CTA when a team is too large for shared memory
 __host__ __device__ constexpr size_t backward_scratch_per_cta(int m, int n)
 {
-    return 2 * (size_t)m * backward_ldn(n) + even_up((size_t)m * backward_ldw(m)) + 2 * even_up((size_t)m * backward_ldf(m));
+    return 2 * (size_t)m * backward_ldn(n) + even_up((size_t)m * backward_ldw(m)) + 2 * even_up((size_t)m * backward_ldf(m))
+           + even_up((size_t)m * (m + 4));  // (Q_uu: only the 16-agent tensor-path kernel keeps it here)
 }
 
 // Shared-memory carve-up in doubles (everything 16-byte aligned).
-__host__ __device__ constexpr BackwardSmem backward_smem(int a, int S, int C, bool mats_in_smem)
+__host__ __device__ constexpr BackwardSmem backward_smem(int a, int S, int C, bool mats_in_smem, bool quu_in_smem = true)
 {
     const int n = a * S, m = a * C, pairs = a * (a - 1) / 2;
     const size_t nblk = (size_t)a * (a + 1) / 2;
     BackwardSmem L{};
     size_t off = 0;
     L.Pb = off;    off += even_up(nblk * (S * S + 2));
-    L.QUU = off;   off += even_up((size_t)m * (m + 4));
+    L.QUU = off;   if (quu_in_smem) off += even_up((size_t)m * (m + 4));
     // the LU work matrix and the packed factors move to the global scratch together with Q_ux / K for big teams
     L.W = off;     if (mats_in_smem) off += even_up((size_t)m * backward_ldw(m));
     L.Lp = off;    if (mats_in_smem) off += even_up((size_t)m * backward_ldf(m));
@@ -123,7 +124,14 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const StageLayout L = stage_layout(a, S, C);
-    const BackwardSmem SM = backward_smem(a, S, C, !GLOBAL);
+    // 16 agents (15 drones + the phantom) leave no room for Q_uu beside P: it joins the other matrices in the scratch
+    constexpr bool QUU_GLOBAL = GLOBAL && AT > 0 && backward_smem(AT > 0 ? AT : 1, S, C, false).total_doubles * 8 > 227 * 1024;
+    const BackwardSmem SM = backward_smem(a, S, C, !GLOBAL, !QUU_GLOBAL);
+    // Odd teams run the tensor-path kernel of the next even size: the stage records carry a PHANTOM agent (A = I,
+    // B = 0, no cost gradient, no proximity term: the zero background of linquad_kernel), whose blocks of P, Q_uu, K
+    // never couple to the real agents' (exact zeros); the descriptor arrays and K, d keep the real team's layout.
+    const int a_real = bt.n_agents;
+    const int n_real = a_real * S, m_real = a_real * C;
 
     double *Pb = smem + SM.Pb;        // [nblk][PBS]   upper-triangular blocks of P
     double *QUU = smem + SM.QUU;      // [m][LDQ]
@@ -151,6 +159,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         W = KB + (size_t)m * LDN;
         Lp = W + even_up((size_t)m * LDW);
         Up = Lp + even_up((size_t)m * backward_ldf(m));
+        if constexpr (QUU_GLOBAL) QUU = Up + even_up((size_t)m * backward_ldf(m));
     } else {
         QUX = smem + SM.mats;
         KB = QUX + (size_t)m * LDN;
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         asm volatile("" : "+r"(v));
         return v;
     };
-    auto cost_row = [&](int i) { return (int64_t)bt.cost_idx[(int64_t)problem() * a + i]; };
+    auto cost_row = [&](int i) { return (int64_t)bt.cost_idx[(int64_t)problem() * a_real + min(i, a_real - 1)]; };  // (the phantom borrows the last agent's cost matrices)
     double *scal = smem + SM.scal;  // [0] mu, [1] weight of the reference cost
     if (threadIdx.x == 0) {
         scal[0] = p.mu[b];
@@ -928,17 +937,17 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         tick(10);
         {
             DPILQR_PHASE_IDS
-        double *Kt = p.K + ((int64_t)problem() * T + t) * m * n;
-        if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(p.K) & 15) == 0) {  // stream K[t] out, coalesced, two entries per access
-            for (int e = tid; e < (m * n) >> 1; e += nthr) {
-                const int k = (2 * e) / n, col = 2 * e - k * n;
+        double *Kt = p.K + ((int64_t)problem() * T + t) * m_real * n_real;
+        if ((n_real & 1) == 0 && (reinterpret_cast<uintptr_t>(p.K) & 15) == 0) {  // stream K[t] out, coalesced, two entries per access
+            for (int e = tid; e < (m_real * n_real) >> 1; e += nthr) {
+                const int k = (2 * e) / n_real, col = 2 * e - k * n_real;
                 const double2 kv = *reinterpret_cast<const double2 *>(KB + (size_t)k * LDN + col);
                 if (!isfinite(kv.x) || !isfinite(kv.y)) st |= DPILQR_ST_NONFINITE;
                 *reinterpret_cast<double2 *>(Kt + 2 * e) = kv;
             }
         } else {
-            for (int e = tid; e < m * n; e += nthr) {
-                const int k = e / n, col = e - k * n;
+            for (int e = tid; e < m_real * n_real; e += nthr) {
+                const int k = e / n_real, col = e - k * n_real;
                 const double kv = KB[(size_t)k * LDN + col];
                 if (!isfinite(kv)) st |= DPILQR_ST_NONFINITE;
                 Kt[e] = kv;
@@ -947,7 +956,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         for (int k = tid; k < m; k += nthr) {
             const double dk = KB[(size_t)k * LDN + n];
             dv[k] = dk;
-            p.d[((int64_t)problem() * T + t) * m + k] = dk;
+            if (k < m_real) p.d[((int64_t)problem() * T + t) * m_real + k] = dk;
         }
         }
         __syncthreads();
@@ -1154,14 +1163,26 @@ static BackwardPlan plan_backward(int a, int s, int c)
     const size_t with_mats = backward_smem(a, s, c, true).total_doubles * 8;
     plan.use_global_scratch = (with_mats > 227 * 1024) ? 1 : 0;
     plan.smem_bytes = plan.use_global_scratch ? backward_smem(a, s, c, false).total_doubles * 8 : with_mats;
+    if (plan.smem_bytes > 227 * 1024 && s == 12 && c == 4 && a == 16)  // the 16-agent tensor-path kernel keeps Q_uu in the scratch
+        plan.smem_bytes = backward_smem(a, s, c, false, false).total_doubles * 8;
     plan.threads = 512;
     return plan;
 }
 
+// Odd Quadcopter12D teams of 5..15 run the tensor-path kernel of the next even size on stage records padded by a
+// phantom agent (see backward_kernel).  The solver asks here which layout its records should have.
+int backward_layout_agents(int a, int s, int c)
+{
+    static const bool no_pad = getenv("DPILQR_BACKWARD_NO_PAD") != nullptr;  // experiments / cross-checks
+    if (!no_pad && s == 12 && c == 4 && (a & 1) && a >= 5 && a <= 15) return a + 1;
+    return a;
+}
+
 int64_t backward_scratch_doubles(int n_problems, int a, int s, int c)
 {
-    const BackwardPlan plan = plan_backward(a, s, c);
-    return plan.use_global_scratch ? (int64_t)n_problems * (int64_t)backward_scratch_per_cta(a * c, a * s) : 0;
+    const int al = backward_layout_agents(a, s, c);
+    const BackwardPlan plan = plan_backward(al, s, c);
+    return plan.use_global_scratch ? (int64_t)n_problems * (int64_t)backward_scratch_per_cta(al * c, al * s) : 0;
 }
 
 // TIMED: the instrumented build of the kernel (per-phase cycle counters); the product build carries no timing code
@@ -1199,13 +1220,19 @@ int launch_backward(const BackwardParams &p_in, int n_blocks, cudaStream_t strea
     p.timing = g_backward_timing;
     p.debug_mode = g_backward_debug_mode;
     const Batch &bt = p.batch;
-    const int a = bt.n_agents, s = bt.s, c = bt.c;
+    const int s = bt.s, c = bt.c;
+    const bool padded = p.a_layout > bt.n_agents;  // records carry a phantom agent: tensor-path kernel of the even size
+    const int a = padded ? p.a_layout : bt.n_agents;
+    if (padded && !(s == 12 && c == 4 && a == bt.n_agents + 1 && (a & 1) == 0 && a >= 6 && a <= 16)) {
+        set_error("backward kernel: no padded path for %d agents in a layout of %d", bt.n_agents, p.a_layout);
+        return DPILQR_E_INVALID;
+    }
     // small problems (DP-iLQR neighbourhoods, small teams): several problems per SM (backward_small.cu)
     static const bool force_big = getenv("DPILQR_BACKWARD_FORCE_BIG") != nullptr;  // experiments / cross-checks
     static const bool no_warp = getenv("DPILQR_BACKWARD_NO_WARP") != nullptr;            // experiments / cross-checks
-    // tiny problems (one or two drones, up to eight planar agents): one warp per problem (backward_warp.cu)
-    if (!force_big && !no_warp && p.timing == nullptr && backward_warp_applies(a, s, c)) return launch_backward_warp(p, n_blocks, stream);
-    if (!force_big && p.timing == nullptr && backward_small_applies(a, s, c)) return launch_backward_small(p, n_blocks, stream);
+    // tiny problems (one or two drones, up to four planar agents): one warp per problem (backward_warp.cu)
+    if (!padded && !force_big && !no_warp && p.timing == nullptr && backward_warp_applies(a, s, c)) return launch_backward_warp(p, n_blocks, stream);
+    if (!padded && !force_big && p.timing == nullptr && backward_small_applies(a, s, c)) return launch_backward_small(p, n_blocks, stream);
     if (a * c > 64) {
         set_error("backward kernel: at most 64 joint controls are supported (got %d)", a * c);
         return DPILQR_E_UNSUPPORTED;
@@ -1221,10 +1248,11 @@ int launch_backward(const BackwardParams &p_in, int n_blocks, cudaStream_t strea
         return DPILQR_E_INVALID;
     }
     if (s == 12 && c == 4) {
-        // tensor-path instantiations: even team sizes (an 8-row tile of the control rows is two agents); 12 and 14
-        // agents keep Q_ux, K and the LU factors in the L2-resident scratch
+        // tensor-path instantiations: even team sizes (an 8-row tile of the control rows is two agents), odd teams
+        // padded by a phantom agent; 12 to 16 agents keep Q_ux, K and the LU factors (16: Q_uu too) in the
+        // L2-resident scratch
         static const bool force_generic = getenv("DPILQR_BACKWARD_FORCE_GENERIC") != nullptr;  // experiments / cross-checks
-        if (!force_generic) {
+        if (!force_generic || padded) {
             if (a == 10 && !plan.use_global_scratch) {
                 if (p.timing != nullptr) return launch_typed<12, 4, 10, false, true>(p, n_blocks, plan, stream);
                 return launch_typed<12, 4, 10, false>(p, n_blocks, plan, stream);
@@ -1233,6 +1261,11 @@ int launch_backward(const BackwardParams &p_in, int n_blocks, cudaStream_t strea
             if (a == 8 && !plan.use_global_scratch) return launch_typed<12, 4, 8, false>(p, n_blocks, plan, stream);
             if (a == 12 && plan.use_global_scratch) return launch_typed<12, 4, 12, true>(p, n_blocks, plan, stream);
             if (a == 14 && plan.use_global_scratch) return launch_typed<12, 4, 14, true>(p, n_blocks, plan, stream);
+            if (a == 16 && plan.use_global_scratch) return launch_typed<12, 4, 16, true>(p, n_blocks, plan, stream);
+        }
+        if (padded) {
+            set_error("backward kernel: padded layout of %d agents has no tensor-path instantiation", a);
+            return DPILQR_E_UNSUPPORTED;
         }
         return launch_generic<12, 4>(p, n_blocks, plan, stream);
     }

@@ -57,6 +57,7 @@ struct LinQuadParams {
     const int32_t *n_active;
     int n_blocks_per_problem;
     int records_per_cta;  // consecutive stage records a CTA builds in shared memory and stores in one bulk copy
+    int a_layout;         // agents of the record LAYOUT (0: the batch's): padded by a phantom agent for odd teams (backward.cu)
 };
 
 struct BackwardParams {
@@ -69,6 +70,7 @@ struct BackwardParams {
     const int32_t *active;
     const int32_t *n_active;
     double *scratch;  // global scratch for the big-problem path (2*m*n doubles per CTA)
+    int a_layout;     // agents of the stage-record layout (0: the batch's); n_agents + 1: records padded by a phantom agent
     int n_launch;     // problems of this launch (kernels whose grid is rounded up to whole CTAs of several problems)
     int use_global_scratch;
     long long *timing;  // optional: 20 per-phase cycle counters written by CTA 0 (debug aid)
@@ -83,6 +85,7 @@ int launch_linquad(const LinQuadParams &p, int n_problems, cudaStream_t stream);
 int launch_stage_to_dense(const Batch &bt, const double *stage, double *A, double *Bm, double *Lx, double *Lu,
                           double *Lxx, double *Luu, cudaStream_t stream);
 int launch_backward(const BackwardParams &p, int n_blocks, cudaStream_t stream);
+int backward_layout_agents(int a, int s, int c);   // agents of the stage-record layout the solver's backward kernel wants
 bool backward_small_applies(int a, int s, int c);
 bool backward_warp_applies(int a, int s, int c);  // tiny problems: one warp per problem (backward_warp.cu)
 int launch_backward_warp(const BackwardParams &p, int n_blocks, cudaStream_t stream);  // backward_small.cu: n <= 64, m <= 32

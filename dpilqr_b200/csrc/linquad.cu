@@ -61,14 +61,15 @@ struct LinquadSmem {
     int recs, ptab, total_doubles;
 };
 
-__host__ __device__ inline LinquadSmem linquad_smem(int a, int s, int c, int rpc)
+// (al: agents of the record layout, a: real agents -- see LinQuadParams::a_layout)
+__host__ __device__ inline LinquadSmem linquad_smem(int al, int a, int s, int c, int rpc)
 {
-    const StageLayout L = stage_layout(a, s, c);
+    const StageLayout L = stage_layout(al, s, c);
     auto even = [](int v) { return (v + 1) & ~1; };
     LinquadSmem M{};
     int off = 0;
     M.recs = off; off += rpc * L.stride;
-    M.ptab = off; off += even(rpc * L.pairs * 10);  // [rec][pair]: inside flag, g[3], H[6]
+    M.ptab = off; off += even(rpc * (a * (a - 1) / 2) * 10);  // [rec][pair]: inside flag, g[3], H[6]
     M.total_doubles = off;
     return M;
 }
@@ -85,10 +86,13 @@ __global__ void __launch_bounds__(kLinquadThreads) linquad_kernel(const LinQuadP
     const int RPC = p.records_per_cta;
     const int t0 = (blockIdx.x % p.n_blocks_per_problem) * RPC;
     const int nrec = min(RPC, T + 1 - t0);
-    const StageLayout L = stage_layout(a, s, c);
-    const LinquadSmem SM = linquad_smem(a, s, c, RPC);
+    // The records may be laid out for one agent more than the team has (a phantom agent with A = I, B = 0 and no cost
+    // terms -- exactly the background below -- lets odd teams use the tensor-path backward kernel of the even size)
+    const int al = p.a_layout > 0 ? p.a_layout : a;
+    const StageLayout L = stage_layout(al, s, c);
+    const LinquadSmem SM = linquad_smem(al, a, s, c, RPC);
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int pairs = L.pairs;
+    const int pairs = a * (a - 1) / 2;
     double *ptab = lq_smem + SM.ptab;
     const int slot = p.slot ? p.slot[b] : 0;
     const double *xbase = p.X + (int64_t)b * p.x_stride + (int64_t)slot * p.x_slot_stride + (int64_t)t0 * n;
@@ -104,8 +108,8 @@ __global__ void __launch_bounds__(kLinquadThreads) linquad_kernel(const LinQuadP
     __syncthreads();
 
     // ---- 2a: A_i = I; one thread per (record, agent pair)
-    for (int k = tid; k < nrec * n; k += nthr) {
-        const int tl = k / n, row = k - tl * n;
+    for (int k = tid; k < nrec * L.n; k += nthr) {  // (L.n: the phantom agent's block too)
+        const int tl = k / L.n, row = k - tl * L.n;
         const int i = row / s, r = row - i * s;
         lq_smem[(size_t)tl * L.stride + L.offA + i * L.strideA + r * s + r] = 1.0;
     }
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(kLinquadThreads) linquad_kernel(const LinQuadP
 #pragma unroll
             for (int k = 0; k < 6; ++k) row[4 + k] = H[k];
             if (inside) {  // off-diagonal block of pair (i, j); zero (the background) outside the radius
-                double *Ho = lq_smem + (size_t)tl * L.stride + L.offHo + 9 * pr;
+                double *Ho = lq_smem + (size_t)tl * L.stride + L.offHo + 9 * pair_index(i, j, al);
                 const double h[6] = {-w_prox * H[0], -w_prox * H[1], -w_prox * H[2], -w_prox * H[3], -w_prox * H[4], -w_prox * H[5]};
                 Ho[0] = h[0]; Ho[1] = h[1]; Ho[2] = h[2];
                 Ho[3] = h[1]; Ho[4] = h[3]; Ho[5] = h[4];
@@ -239,7 +243,8 @@ int launch_linquad(const LinQuadParams &p_in, int n_problems, cudaStream_t strea
     static const int env_threads = getenv("DPILQR_LQ_THREADS") ? atoi(getenv("DPILQR_LQ_THREADS")) : 0;
     static const int env_kb = getenv("DPILQR_LQ_KB") ? atoi(getenv("DPILQR_LQ_KB")) : 0;
     const int threads = env_threads ? env_threads : kLinquadThreads;
-    const size_t one = (size_t)linquad_smem(a, s, c, 1).total_doubles * 8;
+    const int al = p.a_layout > 0 ? p.a_layout : a;
+    const size_t one = (size_t)linquad_smem(al, a, s, c, 1).total_doubles * 8;
     if (one > 200 * 1024 || a > threads) {
         set_error("linearise/quadraticise kernel: a stage record of %d agents does not fit shared memory", a);
         return DPILQR_E_UNSUPPORTED;
@@ -255,7 +260,7 @@ int launch_linquad(const LinQuadParams &p_in, int n_problems, cudaStream_t strea
     rpc = (bt.horizon + 1 + groups - 1) / groups;
     p.records_per_cta = rpc;
     p.n_blocks_per_problem = groups;
-    const size_t smem = (size_t)linquad_smem(a, s, c, rpc).total_doubles * 8;
+    const size_t smem = (size_t)linquad_smem(al, a, s, c, rpc).total_doubles * 8;
     if (smem > 48 * 1024) DPILQR_CUDA(cudaFuncSetAttribute(linquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     linquad_kernel<<<n_problems * p.n_blocks_per_problem, threads, smem, stream>>>(p);
     DPILQR_CUDA(cudaGetLastError());

@@ -74,7 +74,7 @@ static Workspace carve(char *base, int B, int a, int s, int c, int T, int NA)
 {
     Workspace w;
     const int64_t n = (int64_t)a * s, m = (int64_t)a * c;
-    const StageLayout L = stage_layout(a, s, c);
+    const StageLayout L = stage_layout(backward_layout_agents(a, s, c), s, c);  // (odd teams: records padded by a phantom agent)
     int64_t off = 0;
     auto take = [&](int64_t bytes) {
         char *ptr = base ? base + off : nullptr;
@@ -472,6 +472,7 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
         lq.x_stride = NA * xlen; lq.u_stride = NA * ulen; lq.x_slot_stride = xlen; lq.u_slot_stride = ulen;
         lq.slot = w.slot; lq.active = act; lq.n_active = w.n_active;
         lq.stage = w.stage; lq.status = status;
+        lq.a_layout = backward_layout_agents(a, s, c);
         timer.begin(DPILQR_K_LINQUAD, n_act);
         rc = launch_linquad(lq, n_act, stream);
         timer.end();
@@ -481,6 +482,7 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
         bp.batch = *batch;
         bp.stage = w.stage; bp.mu = w.mu; bp.K = w.K; bp.d = w.d; bp.status = status;
         bp.active = act; bp.n_active = w.n_active; bp.scratch = w.scratch;
+        bp.a_layout = lq.a_layout;
         timer.begin(DPILQR_K_BACKWARD, n_act);
         rc = launch_backward(bp, n_act, stream);
         timer.end();

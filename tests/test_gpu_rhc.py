@@ -91,12 +91,14 @@ def test_single_agent_reference_cost_problem():
     assert rel_err(X, Xo) < 1e-8 and rel_err(U, Uo) < 1e-8 and abs(J - Jo) <= 1e-8 * abs(Jo)
 
 
-@pytest.mark.parametrize("a,seed", [(1, 3), (2, 3), (3, 1), (4, 3), (5, 2), (6, 3), (7, 3), (8, 3), (12, 5), (14, 5), (15, 3)])
+@pytest.mark.parametrize("a,seed", [(1, 3), (2, 3), (3, 1), (4, 3), (5, 2), (6, 3), (7, 3), (8, 3), (9, 3), (11, 1), (12, 5), (13, 1), (14, 5), (15, 3)])
 def test_backward_pass_all_sizes_vs_oracle(a, seed):
     """Every code path of the backward kernel (small-problem kernels for up to five drones, tensor path with
     compile-time sizes for 6, 8, 10 drones and -- on the L2 scratch -- 12 and 14, generic DFMA path, generic L2-scratch
     path) against the oracle's _backward_pass on the hover rollout of a random Quadcopter12D scenario and on the
-    iterate after one iLQR iteration (tilted drones, active proximity terms)."""
+    iterate after one iLQR iteration (tilted drones, active proximity terms).  The stand-alone backward pass of an odd
+    team takes the generic kernels; inside the solver loop (the one-iteration solve below, then two more iterations)
+    odd teams of 5..15 run the tensor-path kernel of the next even size on records padded by a phantom agent."""
     import dpilqr_b200 as dp
     from dpilqr_b200 import scenarios
     from oracle import ilqr_oracle as O
@@ -130,6 +132,13 @@ def test_backward_pass_all_sizes_vs_oracle(a, seed):
         eK, ed = rel_err(K[0].cpu().numpy(), K2), rel_err(d[0].cpu().numpy(), d2)
         print(f"a={a}: second-iterate gains K err {eK:.1e} d err {ed:.1e}")
         assert eK < TOL and ed < TOL
+    # three iterations through the solver loop: same accepted step sizes, same iterate
+    out = batch.solve(x0[None], U0[None], n_lqr_iter=3, trace=True)
+    X3, U3, J3 = solver.solve(x0, U0.copy(), n_lqr_iter=3)
+    assert [int(v) for v in out["trace_alpha"][0, :int(out["iters"][0])]] == [r["alpha_index"] for r in solver.trace]
+    e3 = max(rel_err(out["X"][0].cpu().numpy(), X3), rel_err(out["U"][0].cpu().numpy(), U3))
+    print(f"a={a}: three iterations, X/U err {e3:.1e}")
+    assert e3 < 1e-8
 
 
 # --------------------------------------------------------------------------------------------
