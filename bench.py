@@ -348,6 +348,15 @@ def run_gpu_arm(args):
     torch.cuda.synchronize(dev)
     t_compile = time.perf_counter() - t_build
     x0_dev, U0_dev = torch.as_tensor(x0_np).to(dev), torch.as_tensor(U0_np).to(dev)
+    t_device_build = None
+    if args.scaling == "weak":  # the same batch built on the device (scenario kernel + tensor ops): bit-identical inputs
+        scenarios.quad12_batch_device(seeds[0], 8, a, T, dev)
+        torch.cuda.synchronize(dev)
+        t_build = time.perf_counter()
+        _, x0_chk, _ = scenarios.quad12_batch_device(seeds[0], B, a, T, dev)
+        torch.cuda.synchronize(dev)
+        t_device_build = time.perf_counter() - t_build
+        assert torch.equal(x0_chk, x0_dev), "device-built scenarios differ from the host-built ones"
     x0_pin, U0_pin = torch.as_tensor(x0_np).pin_memory(), torch.as_tensor(U0_np).pin_memory()
     fp64_peak = measure_fp64_peak() if rank == 0 else None
     lib = _native.lib()
@@ -490,6 +499,7 @@ def run_gpu_arm(args):
                        "inflight": f"{args.inflight} step(s) in flight per GPU (SolvePipeline: the straggler tail of a step overlaps the bulk "
                                    "of the next; the timed region spans all steps)",
                        "construction_s": {"scenario_inputs_numpy": t_inputs, "CompiledBatch": t_compile,
+                                          "on_the_device_quad12_batch_device": t_device_build,
                                           "note": "outside the timed regions (SURVEY 8d), once per batch"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "path": e2e_path},

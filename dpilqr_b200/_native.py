@@ -85,7 +85,7 @@ EXPORTS = [
     "dpilqr_stage_stride", "dpilqr_workspace_bytes", "dpilqr_f", "dpilqr_integrate", "dpilqr_linearize",
     "dpilqr_rollout_linesearch", "dpilqr_linearize_quadraticize", "dpilqr_game_cost", "dpilqr_stage_to_dense",
     "dpilqr_backward", "dpilqr_inter_graph", "dpilqr_solve_batch", "dpilqr_solve_batch_host", "dpilqr_get_profile", "dpilqr_debug_backward_timing",
-    "dpilqr_release_cache",
+    "dpilqr_release_cache", "dpilqr_random_setup",
 ]
 
 _lib = None
@@ -130,6 +130,7 @@ def lib():
     L.dpilqr_get_profile.argtypes = [ctypes.POINTER(Profile), i32]
     L.dpilqr_debug_backward_timing.argtypes = [vp]
     L.dpilqr_release_cache.restype = i32
+    L.dpilqr_random_setup.argtypes = [i64, i64, i32, i32, i32, dbl, dbl, vp, vp, vp]
     _lib = L
     return L
 

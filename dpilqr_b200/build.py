@@ -17,7 +17,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdpilqr_b200.so")
 # (source, object stem, extra flags): the rollout kernel is compiled once per model / size class (rollout_inst.cu)
 ROLLOUT_CLASSES = [0, 1, 2, 3, 4, 5, 6, 7, 8, 100, 101]
-UNITS = [(src, src[:-3], []) for src in ["solver.cu", "forward.cu", "linquad.cu", "backward.cu", "backward_small.cu", "backward_warp.cu", "graph.cu", "dynamics_api.cu", "cost_api.cu"]]
+UNITS = [(src, src[:-3], []) for src in ["solver.cu", "forward.cu", "linquad.cu", "backward.cu", "backward_small.cu", "backward_warp.cu", "graph.cu", "scenario.cu", "dynamics_api.cu", "cost_api.cu"]]
 UNITS += [("backward_small.cu", f"backward_small_{sc[0]}_{sc[1]}", [f"-DDPILQR_SMALL_S={sc[0]}", f"-DDPILQR_SMALL_C={sc[1]}"])
           for sc in [(12, 4), (6, 3), (4, 2), (3, 2), (5, 2)]]
 UNITS += [("rollout_inst.cu", f"rollout_c{k}", [f"-DDPILQR_ROLLOUT_CLASS={k}"]) for k in ROLLOUT_CLASSES]

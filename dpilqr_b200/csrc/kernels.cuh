@@ -91,6 +91,8 @@ bool backward_warp_applies(int a, int s, int c);  // tiny problems: one warp per
 int launch_backward_warp(const BackwardParams &p, int n_blocks, cudaStream_t stream);  // backward_small.cu: n <= 64, m <= 32
 int launch_backward_small(const BackwardParams &p, int n_blocks, cudaStream_t stream);
 int64_t backward_scratch_doubles(int n_problems, int a, int s, int c);
+int launch_random_setup(int64_t first_seed, int64_t count, int a, int s, int n_d, double var, double energy, double *x0,
+                        double *xf, cudaStream_t stream);  // scenario.cu
 int launch_inter_graph(const double *X, int64_t n_scen, int rows, int a, int s, const double *radius, uint64_t *adj,
                        cudaStream_t stream);
 int launch_game_cost(const Batch &bt, int64_t rows, const double *X, const double *U, int terminal, double *L,

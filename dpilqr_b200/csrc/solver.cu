@@ -754,6 +754,12 @@ int dpilqr_inter_graph(const double *X, int64_t n_scen, int rows, int n_agents, 
     return launch_inter_graph(X, n_scen, rows, n_agents, s, radius, adj, (cudaStream_t)stream);
 }
 
+int dpilqr_random_setup(int64_t first_seed, int64_t count, int n_agents, int n_states, int n_d, double var, double energy,
+                        double *x0, double *xf, void *stream)
+{
+    return launch_random_setup(first_seed, count, n_agents, n_states, n_d, var, energy, x0, xf, (cudaStream_t)stream);
+}
+
 int64_t dpilqr_solve_batch(const dpilqr_batch *batch, const dpilqr_solve_opts *opts, const double *x0, const double *U0,
                            double *X, double *U, double *J, double *J_star, int32_t *iters, int32_t *status,
                            int32_t *trace_alpha, double *trace_mu, double *trace_J, void *workspace,

@@ -205,6 +205,17 @@ int dpilqr_inter_graph(const double *X, int64_t n_scen, int rows, int n_agents, 
                        uint64_t *adj, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Scenario generation: replaces random_setup(n_agents, n_states, n_d=n_d, random=True, var=var,
+ * energy=energy) (reference util.py:165-195 with randomize_locs :125-132, normalize_energy
+ * :203-217, compute_energy :198-200) for the seeds first_seed .. first_seed + count - 1, each
+ * scenario as if preceded by np.random.seed(seed).  Bit-identical to the host path (the kernel
+ * runs NumPy's legacy MT19937 stream and NumPy's reduction orders).  energy <= 0: no normalisation.
+ *   x0, xf [count][n_agents * n_states] out (positions in the first n_d states of each agent).
+ * ------------------------------------------------------------------------------------------ */
+int dpilqr_random_setup(int64_t first_seed, int64_t count, int n_agents, int n_states, int n_d, double var, double energy,
+                        double *x0, double *xf, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Whole solve for a batch: replaces ilqrSolver.solve (reference control.py:150-225) including
  * the regularisation schedule (control.py:227-237).  Synchronous on `stream` at return.
  *   x0 [B][n], U0 [B][T][m] in; X [B][T+1][n], U [B][T][m] out;

@@ -113,3 +113,40 @@ def test_trajectory_metrics_vs_numpy():
         assert np.allclose(m["pairwise"][k].cpu().numpy(), d, rtol=1e-13)
         assert abs(float(m["min_separation"][k]) - d.min()) < 1e-13
         assert int(m["violations"][k]) == int((d < 0.8).sum())
+
+
+@pytest.mark.parametrize("a,s,n_d,var,energy", [(10, 12, 3, 5.0, 30.0), (3, 12, 3, 1.5, 9.0), (15, 12, 3, 7.5, 45.0),
+                                                (5, 4, 2, 3.0, 10.0), (9, 6, 3, 2.0, None), (2, 4, 2, 1.0, 2.0)])
+def test_random_setup_on_the_device_is_bit_identical_to_the_host(a, s, n_d, var, energy):
+    """Scenario generation on the device (reference util.py:125-217, random=True): the kernel runs NumPy's legacy
+    MT19937 stream and NumPy's reduction orders, so x0 and xf equal the host's np.random.seed(k); random_setup(...) bit
+    for bit, for every seed of the batch."""
+    from dpilqr_b200 import scenarios
+    from dpilqr_b200.util import random_setup
+
+    first, count = 7, 300
+    x0, xf = scenarios.random_setup_batch(first, count, a, s, n_d=n_d, var=var, energy=energy)
+    x0, xf = x0.cpu().numpy(), xf.cpu().numpy()
+    for k in range(count):
+        np.random.seed(first + k)
+        h0, hf = random_setup(a, s, is_rotation=False, rel_dist=a, var=var, n_d=n_d, random=True, energy=energy)
+        assert np.array_equal(x0[k], h0.reshape(-1)) and np.array_equal(xf[k], hf.reshape(-1)), (k, np.max(np.abs(x0[k] - h0.reshape(-1))))
+
+
+def test_metric_batch_built_on_the_device_solves_like_the_host_built_one():
+    """quad12_batch_device: descriptor and inputs built by kernels and tensor ops only -- same solve, bit for bit."""
+    import dpilqr_b200 as dp
+    from dpilqr_b200 import scenarios
+
+    specs, x0, U0 = scenarios.quad12_batch(40, 24, 10, 50)
+    host = dp.CompiledBatch(specs, 50).solve(x0, U0)
+    batch, x0d, U0d = scenarios.quad12_batch_device(40, 24, 10, 50)
+    assert np.array_equal(x0d.cpu().numpy(), x0) and np.array_equal(U0d.cpu().numpy(), U0)
+    dev = batch.solve(x0d, U0d)
+    assert torch_equal(dev["X"], host["X"]) and torch_equal(dev["U"], host["U"]) and torch_equal(dev["iters"], host["iters"])
+
+
+def torch_equal(a, b):
+    import torch
+
+    return bool(torch.equal(a, b))
