@@ -231,9 +231,9 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one backward launch over 3908 ten-agent problems
-# (ncu --set full, profiles/r01_backward_ncu_full.txt): extrapolated per problem, not re-measured in the run
-NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM_A10 = (4.180168e9 + 7.515227e9) / 3908
+# dram__bytes_read.sum + dram__bytes_write.sum of one backward launch over 4096 ten-agent problems
+# (ncu --set full, profiles/r02_backward_ncu_full.txt): extrapolated per problem, not re-measured in the run
+NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM_A10 = (4.379636e9 + 7.879973e9) / 4096
 
 
 def measure_fp64_peak():
@@ -509,8 +509,8 @@ def run_gpu_arm(args):
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": (NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM_A10 * bunits / max(blaunch, 1)) if (a == 10 and mode == "potential") else None,
-                         "traffic_source": "EXTRAPOLATED from one ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum = 11.695 GB "
-                                           "for a 3908-problem launch, profiles/r01_backward_ncu_full.txt) to this run's average problems per "
+                         "traffic_source": "EXTRAPOLATED from one ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum = 12.260 GB "
+                                           "for a 4096-problem launch, profiles/r02_backward_ncu_full.txt) to this run's average problems per "
                                            f"launch, not re-measured here; algorithmic bytes/problem = {backward_hbm_bytes(a)}",
                          "peak_source": peak_src,
                          "flops_per_launch_unit": backward_flops(a) if mode == "potential" else None, "launches": blaunch,

@@ -25,6 +25,7 @@ class ilqrSolver:
         self.N = N
         self._batch = None
         self._batch_key = None
+        self._batches = {}
         self._reset_regularization()
 
     # ---- reference properties (control.py:58-78)
@@ -50,13 +51,22 @@ class ilqrSolver:
 
     # ---- engine plumbing
     def _compiled(self, N=None):
+        """Device descriptor of the problem for horizon N.  The reference re-reads problem.dynamics / problem.game_cost on
+        every call; here the flattened spec is fingerprinted (goals, weights, radius, n_dims, cost matrices, dt, models), so a
+        caller that moves the goals or edits a cost between solves gets a fresh descriptor, and one descriptor is kept per
+        horizon (solve_rhc alternates between the planning horizon and its final rollout)."""
         N = self.N if N is None else N
-        cost = self.problem.game_cost
-        key = (N, getattr(cost, "REF_WEIGHT", None), getattr(cost, "PROX_WEIGHT", None))
-        if self._batch is None or self._batch_key != key:
-            self._batch = CompiledBatch([spec_from_problem(self.problem)], N)
-            self._batch_key = key
-        return self._batch
+        spec = spec_from_problem(self.problem)
+        finger = hash((spec.key, tuple(spec.models), tuple(spec.n_dims), spec.xf.tobytes(), float(spec.radius), tuple(spec.weights),
+                       bool(spec.has_prox), tuple(np.asarray(M).tobytes() for M in spec.Q), tuple(np.asarray(M).tobytes() for M in spec.R),
+                       tuple(np.asarray(M).tobytes() for M in spec.Qf)))
+        if self._batch_key != finger:
+            self._batches, self._batch_key = {}, finger
+        batch = self._batches.get(N)
+        if batch is None:
+            batch = self._batches[N] = CompiledBatch([spec], N)
+        self._batch = batch
+        return batch
 
     def _rollout(self, x0, U):
         """Roll the controls out from x0 (reference control.py:80-93)."""

@@ -202,13 +202,19 @@ __global__ void __launch_bounds__(kRolloutMaxThreads, DPILQR_ROLLOUT_MINBLOCKS) 
     const bool staged = GAINS && p.stage_gains;
     double *Ks = smem + o_gains + 2;  // [Ge][m][n]
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + o_gains);
-    auto stage_gains = [&](int t) {  // thread 0, after a block barrier behind the last reads of the previous K
+    // (warp 0, after a block barrier behind the last reads of the previous K.  Lane 0 arms the barrier -- its arrival is
+    // the only one, so the phase cannot complete before the expected byte count is posted -- then the lanes issue the
+    // copies of their groups side by side: with dozens of small problems per CTA one thread issuing every copy was a
+    // quarter of the step.)
+    auto stage_gains = [&](int t) {
         if constexpr (GAINS) {
-            if (staged && t < T && tid == 0) {
+            if (staged && t < T && warp == 0) {
                 const unsigned bytes = (unsigned)(m * n * 8);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * Ge) : "memory");
-                for (int g = 0; g < Ge; ++g)
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * Ge) : "memory");
+                __syncwarp();
+                for (int g = lane; g < Ge; g += 32)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  ::"r"((unsigned)__cvta_generic_to_shared(Ks + (size_t)g * m * n)),
                                    "l"(p.K + ((int64_t)g_prob[g] * T + t) * m * n), "r"(bytes), "r"(mbar) : "memory");
