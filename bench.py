@@ -549,6 +549,68 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_rhc_sharded(args):
+    """The one exchange step of the path: a decentralised receding-horizon run (reference
+    distributed.py:106-221) of ONE 15-drone scenario (BASELINE config 4) whose agents' sub-problems are sharded over the
+    ranks; after every round each rank all-gathers the agents' new trajectories (NCCL over NVLink, one collective per
+    round, dpilqr_b200/parallel.py).  A step is one whole run; rank 0 also checks it against the unsharded run."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dpilqr_b200 as dp
+    from dpilqr_b200 import scenarios
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    a = 15
+    x0, xf, U0 = scenarios.quad12_inputs(0, a, T)
+    dp._reset_ids()
+    ids = [100 + i for i in range(a)]
+    dyn = dp.MultiDynamicalModel([dp.QuadcopterDynamics12D(0.1, id_) for id_ in ids])
+    costs = [dp.ReferenceCost(xf[12 * i:12 * i + 12], np.eye(12), np.eye(4), 1000 * np.eye(12), id_) for i, id_ in enumerate(ids)]
+    prob = dp.ilqrProblem(dyn, dp.GameCost(costs, dp.ProximityCost([12] * a, 0.5, [3] * a)))
+    kw = dict(n_d=3, step_size=5, dist_converge=0.2, t_diverge=1.0, U0=U0, n_lqr_iter=8)
+
+    def run(sharded):
+        return dp.solve_rhc(prob, x0, T, 0.5, [], centralized=False, sharded=sharded and world > 1, **kw)
+
+    for _ in range(args.warmup):
+        run(True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Xs, Us, Js = run(True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    Xr, Ur, Jr = run(False)
+    same = torch.tensor([1 if (np.array_equal(Xs, Xr) and np.array_equal(Us, Ur) and Js == Jr) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    rounds = (Xs.shape[0] - 1) // kw["step_size"] + 1
+    if rank == 0:
+        print(json.dumps({
+            "metric": "decentralised receding-horizon rounds/s (one 15-drone Quadcopter12D scenario, agents sharded over the GPUs)",
+            "value": rounds * args.steps / float(dt), "unit": "rounds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(dt) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE config 4: 15 x Quadcopter12D, solve_rhc(centralized=False, step_size=5, n_lqr_iter=8), seed 0",
+                       "parallelism": f"agents' sub-problems sharded x{world}; one NCCL all-gather of the agents' trajectories per round",
+                       "rounds_per_run": int(rounds), "identical_to_the_unsharded_run_on_every_rank": bool(same.item()),
+                       "note": "latency-bound by construction (one scenario, a handful of sub-problems per rank and round): the record "
+                               "of the path's only collective, not a throughput claim"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -557,7 +619,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenarios", type=int, default=4096, help="scenarios per GPU (weak scaling) or in total (strong scaling)")
     ap.add_argument("--agents", type=int, default=10, choices=[2, 3, 4, 5, 6, 7, 8, 10, 12, 15])
-    ap.add_argument("--mode", default="potential", choices=["potential", "dp"])
+    ap.add_argument("--mode", default="potential", choices=["potential", "dp", "rhc-sharded"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-scenarios", type=int, default=0, help="sample size of the CPU baseline (default 8 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -566,6 +628,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.mode == "rhc-sharded":
+        run_rhc_sharded(args)
     else:
         run_gpu_arm(args)
 
