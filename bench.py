@@ -419,6 +419,8 @@ def run_gpu_arm(args):
     # Steps are issued to a SolvePipeline: `--inflight` solves in flight (worker threads, one stream each); the tail of
     # one step runs beside the bulk of the next (csrc/solver.cu, BulkGate).  The timed region spans all K steps, from
     # before the first is issued until the last has finished.
+    if args.inflight <= 0:  # auto: small batches are latency-bound from the first iteration on, more of them fit side by side
+        args.inflight = 2 if B >= 1024 else 4
     pipe = dp.SolvePipeline(dev, depth=args.inflight)
 
     def run_steps(fn, count):
@@ -446,7 +448,7 @@ def run_gpu_arm(args):
     torch.cuda.synchronize(dev)
     prof = _native.get_profile(reset=True)
     # ---- timed: end to end with host buffers
-    run_steps(step_e2e, min(args.inflight, 2))
+    run_steps(step_e2e, args.inflight)  # (every worker thread's arena and streams exist before the timed region)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -624,7 +626,7 @@ def main():
     ap.add_argument("--cpu-scenarios", type=int, default=0, help="sample size of the CPU baseline (default 8 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2, help="solves in flight per GPU (1 = strictly one after the other)")
+    ap.add_argument("--inflight", type=int, default=0, help="solves in flight per GPU (1 = strictly one after the other; 0 = auto: 2, or 4 for batches under 1024 scenarios)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
