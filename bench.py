@@ -416,11 +416,12 @@ def run_gpu_arm(args):
         d2h = int(sum(t.numel() * t.element_size() for t in out_pin.values()))
         e2e_path = "solve_distributed_round with pinned host tensors in and out"
 
-    # Steps are issued to a SolvePipeline: `--inflight` solves in flight (worker threads, one stream each); the tail of
-    # one step runs beside the bulk of the next (csrc/solver.cu, BulkGate).  The timed region spans all K steps, from
-    # before the first is issued until the last has finished.
-    if args.inflight <= 0:  # auto: small batches are latency-bound from the first iteration on, more of them fit side by side
-        args.inflight = 2 if B >= 1024 else 4
+    # Steps are issued to a SolvePipeline: `--inflight` solves in flight (worker threads, one stream each): their
+    # launches interleave and the straggler tail of a step runs, on a high-priority stream, beside the next steps
+    # (csrc/solver.cu).  The timed region spans all K steps, from before the first is issued until the last has finished.
+    ws_bytes = int(lib.dpilqr_workspace_bytes(B, a, S, C, T, 10))
+    if args.inflight <= 0:  # auto: three steps in flight, four for small (latency-bound) batches, within 100 GB of workspaces
+        args.inflight = max(1, min(3 if B >= 1024 else 4, int(100e9 // max(ws_bytes, 1))))
     pipe = dp.SolvePipeline(dev, depth=args.inflight)
 
     def run_steps(fn, count):
@@ -447,6 +448,7 @@ def run_gpu_arm(args):
         step_resident(profile=True)
     torch.cuda.synchronize(dev)
     prof = _native.get_profile(reset=True)
+    torch.cuda.empty_cache()  # the resident arm's cached workspaces make room for the host-buffer arm's arenas
     # ---- timed: end to end with host buffers
     run_steps(step_e2e, args.inflight)  # (every worker thread's arena and streams exist before the timed region)
     barrier()
@@ -498,8 +500,8 @@ def run_gpu_arm(args):
                        "iterations_per_step": iters / args.steps / world,
                        "l2": "working set per step (gains, candidate trajectories, stage records: GBs) >> 126 MB L2",
                        "parallelism": f"scenario-sharded x{world} ({args.scaling} scaling), no data-path collective",
-                       "inflight": f"{args.inflight} step(s) in flight per GPU (SolvePipeline: the straggler tail of a step overlaps the bulk "
-                                   "of the next; the timed region spans all steps)",
+                       "inflight": f"{args.inflight} step(s) in flight per GPU (SolvePipeline: the launches of the steps interleave, the straggler "
+                                   "tail of a step runs beside the next steps; the timed region spans all steps)",
                        "construction_s": {"scenario_inputs_numpy": t_inputs, "CompiledBatch": t_compile,
                                           "on_the_device_quad12_batch_device": t_device_build,
                                           "note": "outside the timed regions (SURVEY 8d), once per batch"}},
@@ -626,7 +628,7 @@ def main():
     ap.add_argument("--cpu-scenarios", type=int, default=0, help="sample size of the CPU baseline (default 8 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--inflight", type=int, default=0, help="solves in flight per GPU (1 = strictly one after the other; 0 = auto: 2, or 4 for batches under 1024 scenarios)")
+    ap.add_argument("--inflight", type=int, default=0, help="solves in flight per GPU (1 = strictly one after the other; 0 = auto: 3, or 4 for batches under 1024 scenarios, within 100 GB of workspaces)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -392,11 +392,12 @@ def solve_specs(specs, x0s, U0s, N, device=None, on_error="raise", **kw):
 class SolvePipeline:
     """Keeps ``depth`` batched solves in flight on one device (not in the reference, whose batches are a process pool).
 
-    One worker thread and one CUDA stream per solve in flight.  The library makes concurrent callers take turns for the
-    bulk of a solve -- the launches that fill the machine -- and runs the tail of a solve (the few problems that need many
-    more iterations than the rest: a tenth of the time of a 4096-scenario batch for 1.5 % of its work) on a
-    high-priority stream beside the next solve's bulk (csrc/solver.cu, BulkGate).  Throughput of a stream of batches
-    then follows their work rather than the latency of their stragglers.
+    One worker thread and one CUDA stream per solve in flight.  The launches of concurrent solves interleave -- the
+    line-search launches are bound by the latency of their 51-step chains, not by the machine -- and the library runs
+    the tail of a solve (the few problems that need many more iterations than the rest: a tenth of the time of a
+    4096-scenario batch for 3 % of its work) on a high-priority stream beside the other solves (csrc/solver.cu).
+    Throughput of a stream of batches then follows their work rather than the latency of their stragglers.  Each solve
+    in flight holds its own workspace (18 GB for 4096 ten-drone scenarios).
 
         pipe = SolvePipeline(device, depth=2)
         for out in pipe.map(lambda args: batch.solve(*args), jobs): ...
