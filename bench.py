@@ -471,6 +471,7 @@ def run_gpu_arm(args):
         value = iters / (ms * 1e-3)
         e2e_value = iters_e2e / (ms_e2e * 1e-3)
         bms, blaunch, bunits = prof["backward"]
+        fms, flaunch, funits = prof["backward_full"]
         lms, llaunch, lunits = prof["linesearch"]
         if mode == "potential":
             bflops = backward_flops(a) * bunits
@@ -487,7 +488,7 @@ def run_gpu_arm(args):
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             pass
-        total_ms = sum(v[0] for v in prof.values())
+        total_ms = sum(v[0] for k, v in prof.items() if k != "backward_full")
         kname = f"backward_kernel<12,4,{a}>" if mode == "potential" else "backward_kernel<12,4,k> over the neighbourhood sizes k"
         per_gpu = B
         line = {
@@ -507,11 +508,14 @@ def run_gpu_arm(args):
                                           "note": "outside the timed regions (SURVEY 8d), once per batch"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "path": e2e_path},
-            "gpu_launches": int(sum(v[1] for v in prof.values()) / n_prof * args.steps),
+            "gpu_launches": int(sum(v[1] for k, v in prof.items() if k != "backward_full") / n_prof * args.steps),
             "clocks": clocks,
             "roofline": {"kernel": kname, "bound": "tensor", "bound_detail": "FP64 pipe: mma.sync.m8n8k4.f64 tiles + DFMA",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
+                         "frac_of_the_launches_that_fill_the_machine": (backward_flops(a) * funits / (fms * 1e-3) * 1e-12 / peak)
+                         if (mode == "potential" and fms > 0) else None,
+                         "launches_that_fill_the_machine": flaunch,
                          "traffic": (NCU_BACKWARD_DRAM_BYTES_PER_PROBLEM_A10 * bunits / max(blaunch, 1)) if (a == 10 and mode == "potential") else None,
                          "traffic_source": "EXTRAPOLATED from one ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum = 12.260 GB "
                                            "for a 4096-problem launch, profiles/r02_backward_ncu_full.txt) to this run's average problems per "
@@ -526,7 +530,7 @@ def run_gpu_arm(args):
                                     "note": "algorithmic bytes = gains read once per problem-iteration + trajectories; the kernel is bound by "
                                             "the latency of the serial RK4 chain, not by either roofline (DESIGN.md)",
                                     "share_of_step": lms / total_ms if total_ms else None},
-            "kernel_ms_per_step": dict({k: v[0] / n_prof for k, v in prof.items()},
+            "kernel_ms_per_step": dict({k: v[0] / n_prof for k, v in prof.items() if k != "backward_full"},
                                        note=f"{n_prof} step(s) run one at a time after the timed region, every launch between CUDA events"),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -61,13 +61,13 @@ class SolveOpts(ctypes.Structure):
     ]
 
 
-KERNEL_KINDS = ["rollout", "linquad", "backward", "linesearch", "select"]
+KERNEL_KINDS = ["rollout", "linquad", "backward", "linesearch", "select", "backward_full"]
 
 
 class Profile(ctypes.Structure):
     """Mirror of ``dpilqr_profile``."""
 
-    _fields_ = [("ms", ctypes.c_double * 5), ("launches", ctypes.c_int64 * 5), ("units", ctypes.c_int64 * 5)]
+    _fields_ = [("ms", ctypes.c_double * 6), ("launches", ctypes.c_int64 * 6), ("units", ctypes.c_int64 * 6)]
 
 
 # status bits (include/dpilqr_b200.h)

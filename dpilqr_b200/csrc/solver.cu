@@ -281,6 +281,17 @@ __global__ void gather_result_kernel(int B, int64_t xlen, int64_t ulen, int NA, 
 static std::mutex g_profile_lock;
 static dpilqr_profile g_profile = {};
 
+static int sm_count()
+{
+    static int count = 0;
+    if (count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || count <= 0) count = 148;
+    }
+    return count;
+}
+
 struct LaunchTimer {
     bool on;
     cudaStream_t stream;
@@ -310,6 +321,11 @@ struct LaunchTimer {
                 g_profile.ms[r.kind] += ms;
                 g_profile.launches[r.kind] += 1;
                 g_profile.units[r.kind] += r.units;
+                if (r.kind == DPILQR_K_BACKWARD && r.units >= sm_count()) {  // launches that fill the machine
+                    g_profile.ms[DPILQR_K_BACKWARD_FULL] += ms;
+                    g_profile.launches[DPILQR_K_BACKWARD_FULL] += 1;
+                    g_profile.units[DPILQR_K_BACKWARD_FULL] += r.units;
+                }
             }
             cudaEventDestroy(r.e0);
             cudaEventDestroy(r.e1);

@@ -119,7 +119,8 @@ enum {
     DPILQR_K_BACKWARD = 2,   /* kernel 3 */
     DPILQR_K_LINESEARCH = 3, /* kernel 1 with gains, all candidates */
     DPILQR_K_SELECT = 4,     /* accept / regularisation / compaction */
-    DPILQR_K_COUNT = 5
+    DPILQR_K_BACKWARD_FULL = 5, /* the kernel-3 launches with at least one problem per SM (counted in kind 2 as well) */
+    DPILQR_K_COUNT = 6
 };
 
 /* accumulated since the last reset: device milliseconds, number of launches and number of problems
