@@ -457,7 +457,7 @@ int launch_small_sc(const BackwardParams &p, int n_blocks, cudaStream_t stream)
     const int a = p.batch.n_agents, m = a * C;
     const size_t smem = (size_t)small_smem(a, S, C).total_doubles * 8;
     auto go = [&](auto kernel) -> int {
-        if (smem > 48 * 1024) DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))  /* the ceiling, not this launch's need: concurrent callers must not lower it under each other */;
         kernel<<<n_blocks, kSmallThreads, smem, stream>>>(p);
         DPILQR_CUDA(cudaGetLastError());
         return DPILQR_OK;

@@ -367,7 +367,7 @@ int launch_warp_one(const BackwardParams &p, int n_blocks, cudaStream_t stream)
         const size_t smem = (size_t)warp_smem(A, S, C).total_doubles * 8 * kWarpKernelWarps;
         const int grid = (n_blocks + kWarpKernelWarps - 1) / kWarpKernelWarps;
         auto kernel = backward_warp_kernel<S, C, A>;
-        if (smem > 48 * 1024) DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))  /* the ceiling, not this launch's need: concurrent callers must not lower it under each other */;
         kernel<<<grid, 32 * kWarpKernelWarps, smem, stream>>>(p);
         DPILQR_CUDA(cudaGetLastError());
         return DPILQR_OK;

@@ -261,7 +261,7 @@ int launch_linquad(const LinQuadParams &p_in, int n_problems, cudaStream_t strea
     p.records_per_cta = rpc;
     p.n_blocks_per_problem = groups;
     const size_t smem = (size_t)linquad_smem(al, a, s, c, rpc).total_doubles * 8;
-    if (smem > 48 * 1024) DPILQR_CUDA(cudaFuncSetAttribute(linquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) DPILQR_CUDA(cudaFuncSetAttribute(linquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))  /* the ceiling, not this launch's need: concurrent callers must not lower it under each other */;
     linquad_kernel<<<n_problems * p.n_blocks_per_problem, threads, smem, stream>>>(p);
     DPILQR_CUDA(cudaGetLastError());
     return DPILQR_OK;

@@ -630,7 +630,8 @@ int launch_rollout_one(ForwardParams p, const RolloutPlan &plan, cudaStream_t st
     p.stage_gains = plan.stage_gains;
     auto kernel = rollout_kernel<MC, NAMAX, GAINS>;
     if (plan.smem > 48 * 1024)
-        DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        // (the ceiling, not this launch's need: concurrent callers must not lower it under each other)
+        DPILQR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kernel<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
     DPILQR_CUDA(cudaGetLastError());
     return DPILQR_OK;
