@@ -77,9 +77,17 @@ __host__ __device__ inline RolloutSmem rollout_smem(int a, int s, int c, int G, 
 #ifndef DPILQR_ROLLOUT_MINBLOCKS
 #define DPILQR_ROLLOUT_MINBLOCKS 2
 #endif
+#ifndef DPILQR_ROLLOUT_TEAM_THREADS
+#define DPILQR_ROLLOUT_TEAM_THREADS 256  // experiment: 192 = exactly two teams, three CTAs per SM (-DDPILQR_ROLLOUT_TEAM_MINBLOCKS=3)
+#endif
+#ifndef DPILQR_ROLLOUT_TEAM_MINBLOCKS
+#define DPILQR_ROLLOUT_TEAM_MINBLOCKS DPILQR_ROLLOUT_MINBLOCKS
+#endif
+__host__ __device__ constexpr int rollout_max_threads(int mc) { return rollout_team_mode(mc) ? DPILQR_ROLLOUT_TEAM_THREADS : kRolloutMaxThreads; }
+__host__ __device__ constexpr int rollout_min_blocks(int mc) { return rollout_team_mode(mc) ? DPILQR_ROLLOUT_TEAM_MINBLOCKS : DPILQR_ROLLOUT_MINBLOCKS; }
 
 template <int MC, int NAMAX, bool GAINS>
-__global__ void __launch_bounds__(kRolloutMaxThreads, DPILQR_ROLLOUT_MINBLOCKS) rollout_kernel(const ForwardParams p)
+__global__ void __launch_bounds__(rollout_max_threads(MC), rollout_min_blocks(MC)) rollout_kernel(const ForwardParams p)
 {
     extern __shared__ __align__(16) double smem[];
     const Batch &bt = p.batch;
@@ -599,7 +607,8 @@ inline RolloutPlan plan_rollout(int a, int s, int c, int n_alpha, int n_list, in
     int gain_warps = G * row_tasks_per_group;
     if (gain_warps > 8) gain_warps = 8;
     if (gains && threads < 32 * gain_warps) threads = 32 * gain_warps;
-    if (threads > kRolloutMaxThreads) threads = kRolloutMaxThreads;
+    const int max_threads = team ? DPILQR_ROLLOUT_TEAM_THREADS : kRolloutMaxThreads;
+    if (threads > max_threads) threads = max_threads;
     plan.G = G;
     plan.threads = threads;
     plan.chunk_alpha = NA;
