@@ -4,10 +4,10 @@
 // Same recursion as backward.cu (reference ilqrSolver._backward_pass, control.py:116-148); this is the kernel of the
 // DP-iLQR sub-problems -- nine in ten neighbourhoods hold one to three agents -- and of small
 // teams in general, for which one 512-thread CTA per SM (backward.cu) leaves the machine idle.  Everything of a
-// problem lives in shared memory for the whole recursion (P dense and double-buffered, 8 to 100 kB per problem, so
-// 2 to 16 problems share an SM); per time step
+// problem lives in shared memory for the whole recursion (P dense, updated in place; 5 to 70 kB per problem, so 3 to 16
+// problems share an SM); per time step
 //   A   S = B^T (P + mu I) (block-diagonal B: C rows per agent),  Q_ux = S A,  Q_uu = L_uu + S B,  Q_u, Q_x
-//   B   Q_xx = L_xx + A^T P A on the upper blocks, one thread per (block, column), into the second P buffer
+//   B   Q_xx = L_xx + A^T P A on the upper blocks, one thread per (block, column), in place (whole blocks per round)
 //   C   LU of Q_uu with partial pivoting by ONE warp, a row per lane (m <= 32): exact arg-max pivot (two redux steps
 //       on the magnitude's bit pattern) -- runs beside phase B
 //   D   K = -Q_uu^{-1} Q_ux, d = -Q_uu^{-1} Q_u: one thread per right-hand side, four rows at a time in registers
@@ -21,7 +21,7 @@
 namespace dpilqr {
 
 struct SmallSmem {
-    int P0, P1, QUX, KB, QUU, W, rec, pvec, Qx, pq, Qu, dv, zv, order, total_doubles, ldp, ldn, ldq;
+    int P0, QUX, KB, QUU, W, rec, pvec, Qx, pq, Qu, dv, zv, order, total_doubles, ldp, ldn, ldq;
 };
 
 __host__ __device__ inline SmallSmem small_smem(int a, int s, int c)
@@ -33,8 +33,7 @@ __host__ __device__ inline SmallSmem small_smem(int a, int s, int c)
     L.ldn = even(n + 1) + 2;  // row stride of Q_ux / K: column n carries Q_u / d
     L.ldq = m | 1;            // row stride of Q_uu and of the LU factors: odd, so a column walks distinct banks
     int off = 0;
-    L.P0 = off;   off += n * L.ldp;
-    L.P1 = off;   off += n * L.ldp;
+    L.P0 = off;   off += n * L.ldp;  // P in place: Q_xx overwrites it block by block (round 2: was double-buffered)
     L.QUX = off;  off += m * L.ldn;
     L.KB = off;   off += m * L.ldn;
     L.QUU = off;  off += even(m * L.ldq);
@@ -72,7 +71,7 @@ __global__ void __launch_bounds__(kSmallThreads) backward_small_kernel(const Bac
     const StageLayout L = stage_layout(a, S, C);
     const SmallSmem SM = small_smem(a, S, C);
     const int LDP = SM.ldp, LDN = SM.ldn, LDQ = SM.ldq;
-    double *Pcur = smem + SM.P0, *Pnxt = smem + SM.P1;
+    double *Pcur = smem + SM.P0, *Pnxt = Pcur;  // one buffer: phase B reads a block before it overwrites it
     double *QUX = smem + SM.QUX;  // [m][LDN]  S, then Q_ux (col n: Q_u), then Y
     double *KB = smem + SM.KB;    // [m][LDN]  S staging, then K (col n: d)
     double *QUU = smem + SM.QUU;  // [m][LDQ]
@@ -217,43 +216,57 @@ __global__ void __launch_bounds__(kSmallThreads) backward_small_kernel(const Bac
                 __syncwarp();
             }
         } else {
-            // phase B: Q_xx = L_xx + A^T P A on the upper blocks -> Pnxt (mirrored below the diagonal)
+            // phase B: Q_xx = L_xx + A^T P A on the upper blocks, IN PLACE (mirrored below the diagonal).  A round takes
+            // whole blocks (one thread per block column): every thread of the round reads its block (V = P_ij A_j, a
+            // column in registers), the group meets at a named barrier, then the columns of Q_xx overwrite the block
+            // (and its mirror image, which phase B never reads).
             constexpr int gn = nthr - 32;
+            constexpr int blocks_per_round = gn / S;
             const int gt = tid - 32;
-            for (int it = gt; it < nblk * S; it += gn) {
-                const int blk = it / S, sg = it - blk * S;
-                int i = 0, rem = blk;
+            const bool worker = gt < blocks_per_round * S;
+            for (int blk0 = 0; blk0 < nblk; blk0 += blocks_per_round) {
+                const int blk = blk0 + gt / S, sg = gt % S;
+                const bool live = worker && blk < nblk;
+                int i = 0, rem = live ? blk : 0;
                 while (rem >= a - i) { rem -= a - i; ++i; }
                 const int j = i + rem;
-                const double *Pblk = Pcur + (size_t)(i * S) * LDP + j * S;
-                const double *Ai = sA + i * L.strideA, *Aj = sA + j * L.strideA;
-                double acol[S], v[S];
+                double v[S];
+                if (live) {
+                    const double *Pblk = Pcur + (size_t)(i * S) * LDP + j * S;
+                    const double *Aj = sA + j * L.strideA;
+                    double acol[S];
 #pragma unroll
-                for (int q = 0; q < S; ++q) acol[q] = Aj[q * S + sg];
+                    for (int q = 0; q < S; ++q) acol[q] = Aj[q * S + sg];
 #pragma unroll
-                for (int r = 0; r < S; ++r) {
-                    double acc = 0.0;
+                    for (int r = 0; r < S; ++r) {
+                        double acc = 0.0;
 #pragma unroll
-                    for (int q = 0; q < S; ++q) acc = fma(Pblk[r * LDP + q], acol[q], acc);
-                    v[r] = acc;
-                }
-#pragma unroll
-                for (int r = 0; r < S; ++r) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int q = 0; q < S; ++q) acc = fma(Ai[q * S + r], v[q], acc);
-                    double lxx = 0.0;
-                    if (i == j) {
-                        const double *Q = bt.Q + (int64_t)cidx[i] * S * S;
-                        lxx = w_ref * (Q[r * S + sg] + Q[sg * S + r]);
-                        if (r < 3 && sg < 3) lxx += sHd[9 * i + r * 3 + sg];
-                    } else if (r < 3 && sg < 3) {
-                        lxx = sHo[9 * pair_index(i, j, a) + r * 3 + sg];
+                        for (int q = 0; q < S; ++q) acc = fma(Pblk[r * LDP + q], acol[q], acc);
+                        v[r] = acc;
                     }
-                    const double q = lxx + acc;
-                    Pnxt[(size_t)(i * S + r) * LDP + j * S + sg] = q;
-                    if (i != j) Pnxt[(size_t)(j * S + sg) * LDP + i * S + r] = q;
                 }
+                asm volatile("bar.sync 2, %0;" ::"n"(gn) : "memory");  // every block of the round has been read
+                if (live) {
+                    const double *Ai = sA + i * L.strideA;
+#pragma unroll
+                    for (int r = 0; r < S; ++r) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int q = 0; q < S; ++q) acc = fma(Ai[q * S + r], v[q], acc);
+                        double lxx = 0.0;
+                        if (i == j) {
+                            const double *Q = bt.Q + (int64_t)cidx[i] * S * S;
+                            lxx = w_ref * (Q[r * S + sg] + Q[sg * S + r]);
+                            if (r < 3 && sg < 3) lxx += sHd[9 * i + r * 3 + sg];
+                        } else if (r < 3 && sg < 3) {
+                            lxx = sHo[9 * pair_index(i, j, a) + r * 3 + sg];
+                        }
+                        const double q = lxx + acc;
+                        Pnxt[(size_t)(i * S + r) * LDP + j * S + sg] = q;
+                        if (i != j) Pnxt[(size_t)(j * S + sg) * LDP + i * S + r] = q;
+                    }
+                }
+                // (no barrier before the next round: it reads upper blocks nobody has written -- the mirrors land below the diagonal)
             }
         }
         __syncthreads();
@@ -443,9 +456,6 @@ __global__ void __launch_bounds__(kSmallThreads) backward_small_kernel(const Bac
                 pvec[col] = pnew;
             }
         }
-        double *tmp = Pcur;
-        Pcur = Pnxt;
-        Pnxt = tmp;
         // (the barrier at the top of the next step orders phase F before its readers)
     }
     if (st != 0 && p.status) atomicOr(p.status + b, st);
