@@ -501,7 +501,7 @@ static int64_t solve_device(const dpilqr_batch *batch, const dpilqr_solve_opts *
             bounds[2] = NA < 3 ? NA : 3;
             bounds[3] = four_stages ? (NA < 5 ? NA : 5) : NA;
         }
-        const double expect[kMaxStages] = {1.0, 0.45, 0.3, 0.18};  // share of the active problems that reaches each stage (metric batch)
+        const double expect[kMaxStages] = {1.0, 0.45, 0.27, 0.16};  // share of the active problems that reaches each stage (metric batch)
         const int32_t *list_in = act;
         const int32_t *count_in = w.n_active;
         timer.begin(DPILQR_K_LINESEARCH, n_act);
