@@ -32,6 +32,14 @@
 
 namespace dpilqr {
 
+// Experiment (-DDPILQR_UPPER_INVERSE=1): the 8x8 diagonal blocks of U applied as explicit inverses on the tensor path in
+// the backward substitution of phase D, like those of L (default: substituted through by eight lanes -- U carries the
+// conditioning of Q_uu and the inverse costs accuracy in K).
+#ifndef DPILQR_UPPER_INVERSE
+#define DPILQR_UPPER_INVERSE 0
+#endif
+constexpr bool kUpperInverse = DPILQR_UPPER_INVERSE != 0;
+
 template <int S>
 struct TileSize {
     static constexpr int value = (S % 4 == 0) ? 4 : (S % 3 == 0) ? 3 : S;
@@ -742,9 +750,10 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             // thread per (block, column of the inverse).
             constexpr int M = AT * C, NB = M / 8;
             __syncthreads();
-            const int bb = tid >> 3, j = tid & 7;
+            const int bb = (tid & 63) >> 3, j = tid & 7;
             double x[8];
             const bool busy = tid < NB * 8;
+            const bool busy_u = kUpperInverse && tid >= 64 && tid < 64 + NB * 8;  // (NB <= 8: the two groups are disjoint)
             if (busy) {
                 const double *F = Lp + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = l(rr, c) of this block
 #pragma unroll
@@ -754,11 +763,23 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     for (int c = 0; c < i; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
                     x[i] = acc;
                 }
+            } else if (busy_u) {
+                const double *F = Up + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = u(rr, c), rr <= c
+#pragma unroll
+                for (int i = 7; i >= 0; --i) {  // upper: solve U x = e_j by back substitution (x_i = 0 for i > j)
+                    double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int c = i + 1; c < 8; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
+                    x[i] = (i <= j) ? acc * rdiag[8 * bb + i] : 0.0;
+                }
             }
             __syncthreads();
             if (busy) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) Lp[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j), same transposed layout
+            } else if (busy_u) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Up[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j); zero below the diagonal
             }
         }
         }
@@ -823,7 +844,17 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     // The diagonal block is substituted through by lanes 0..7 (one right-hand side each).  Its explicit
                     // inverse would be one more tensor instruction pair, but U carries the conditioning of Q_uu and
                     // the inverse costs about a digit of accuracy in K.
-                    if (lane < 8) {
+                    if constexpr (kUpperInverse) {
+                        // X_b <- inv(U_bb) X_b on the tensor path (the inverse was formed with the pack)
+                        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            dmma_m8n8k4(d0, d1, Up[(8 * blk + 4 * ks + fc) * LDF + 8 * blk + fr],
+                                        Xc[(size_t)(8 * blk + 4 * ks + fc) * LDN + fr]);
+                        __syncwarp();
+                        xc[blk] = make_double2(d0, d1);
+                        *reinterpret_cast<double2 *>(Xc + (size_t)(8 * blk + fr) * LDN + 2 * fc) = xc[blk];
+                    } else if (lane < 8) {
                         double x[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) x[j] = Xc[(size_t)(8 * blk + j) * LDN + lane];
