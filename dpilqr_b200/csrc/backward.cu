@@ -32,11 +32,14 @@
 
 namespace dpilqr {
 
-// Experiment (-DDPILQR_UPPER_INVERSE=1): the 8x8 diagonal blocks of U applied as explicit inverses on the tensor path in
-// the backward substitution of phase D, like those of L (default: substituted through by eight lanes -- U carries the
-// conditioning of Q_uu and the inverse costs accuracy in K).
+// The 8x8 diagonal blocks of U are applied as explicit inverses on the tensor path in the backward substitution of phase D,
+// like those of L (-DDPILQR_UPPER_INVERSE=0: substituted through by eight lanes, a serial chain that was 6 % of the
+// kernel's samples).  U carries the conditioning of Q_uu, so the inverse costs a little accuracy -- measured on the metric
+// family: K, d at t = 0 against the reference 1.4e-14 / 4.3e-14 instead of 1.0e-14 / 1.1e-14, the same 118 of 125
+// scenarios of the bench's parity sample within 1e-9 (median 6.6e-13), crowded scenarios (cond 3e9) inside their bar --
+// for 2.8 % of the kernel's time.
 #ifndef DPILQR_UPPER_INVERSE
-#define DPILQR_UPPER_INVERSE 0
+#define DPILQR_UPPER_INVERSE 1
 #endif
 constexpr bool kUpperInverse = DPILQR_UPPER_INVERSE != 0;
 
@@ -336,16 +339,15 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         // residue is not damped by the recursion (it propagates with the open-loop A^T . A and grew by about 12 % per
         // time step on Quadcopter12D, costing two to three digits of K and d at t = 0).
         {
-            constexpr int NPAIR = S * (S - 1) / 2;
-            for (int k = tid; k < a * NPAIR; k += nthr) {
-                const int i = k / NPAIR;
-                int r = 0, rem = k - i * NPAIR;
-                while (rem >= S - 1 - r) { rem -= S - 1 - r; ++r; }
-                const int cc = r + 1 + rem;
-                double *blk = Pb + (size_t)blk_index(i, i) * PBS;
-                const double v = 0.5 * (blk[r * S + cc] + blk[cc * S + r]);
-                blk[r * S + cc] = v;
-                blk[cc * S + r] = v;
+            for (int k = tid; k < a * S * S; k += nthr) {  // one item per entry, the upper ones act (constant divisors only)
+                const int i = k / (S * S), e = k - i * (S * S);
+                const int r = e / S, cc = e - r * S;
+                if (r < cc) {
+                    double *blk = Pb + (size_t)blk_index(i, i) * PBS;
+                    const double v = 0.5 * (blk[e] + blk[cc * S + r]);
+                    blk[e] = v;
+                    blk[cc * S + r] = v;
+                }
             }
         }
         // Regularise P in place for phase A (P + mu I, control.py:134-135); the plain diagonal waits in pq (free until
@@ -841,9 +843,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 for (int blk = NB - 1; blk >= 0; --blk) {
                     *reinterpret_cast<double2 *>(Xc + (size_t)(8 * blk + fr) * LDN + 2 * fc) = xc[blk];
                     __syncwarp();
-                    // The diagonal block is substituted through by lanes 0..7 (one right-hand side each).  Its explicit
-                    // inverse would be one more tensor instruction pair, but U carries the conditioning of Q_uu and
-                    // the inverse costs about a digit of accuracy in K.
+                    // The diagonal block: its explicit inverse (formed with the pack) on the tensor path, or -- the
+                    // fallback build -- substituted through by lanes 0..7, one right-hand side each.
                     if constexpr (kUpperInverse) {
                         // X_b <- inv(U_bb) X_b on the tensor path (the inverse was formed with the pack)
                         double d0 = 0.0, d1 = 0.0;
@@ -968,22 +969,6 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         tick(10);
         {
             DPILQR_PHASE_IDS
-        double *Kt = p.K + ((int64_t)problem() * T + t) * m_real * n_real;
-        if ((n_real & 1) == 0 && (reinterpret_cast<uintptr_t>(p.K) & 15) == 0) {  // stream K[t] out, coalesced, two entries per access
-            for (int e = tid; e < (m_real * n_real) >> 1; e += nthr) {
-                const int k = (2 * e) / n_real, col = 2 * e - k * n_real;
-                const double2 kv = *reinterpret_cast<const double2 *>(KB + (size_t)k * LDN + col);
-                if (!isfinite(kv.x) || !isfinite(kv.y)) st |= DPILQR_ST_NONFINITE;
-                *reinterpret_cast<double2 *>(Kt + 2 * e) = kv;
-            }
-        } else {
-            for (int e = tid; e < m_real * n_real; e += nthr) {
-                const int k = e / n_real, col = e - k * n_real;
-                const double kv = KB[(size_t)k * LDN + col];
-                if (!isfinite(kv)) st |= DPILQR_ST_NONFINITE;
-                Kt[e] = kv;
-            }
-        }
         for (int k = tid; k < m; k += nthr) {
             const double dk = KB[(size_t)k * LDN + n];
             dv[k] = dk;
@@ -998,6 +983,30 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         // The stage record of this step has been dead since the warp groups joined: fetch the next one behind phases E
         // and F.  The last thread issues the copies -- its warp has nothing to do in the vector phase below.
         if (t > 0) prefetch_record(t - 1, nthr - 1);
+        // K[t] streams out to HBM on the threads that have no column in the vector phase below (K stays in shared
+        // memory until phase A of the next step reuses the buffer).  (One TMA bulk store per row, issued by a warp and
+        // left to complete behind phases E and F, measured slower: the issuing warp holds the phase up.)
+        {
+            double *Kt = p.K + ((int64_t)problem() * T + t) * m_real * n_real;
+            const int first = (n + m < nthr - 64) ? n + m : 0, nw = nthr - first;
+            if (tid >= first) {
+                if ((n_real & 1) == 0 && (reinterpret_cast<uintptr_t>(p.K) & 15) == 0) {  // coalesced, two entries per access
+                    for (int e = tid - first; e < (m_real * n_real) >> 1; e += nw) {
+                        const int k = (2 * e) / n_real, col = 2 * e - k * n_real;
+                        const double2 kv = *reinterpret_cast<const double2 *>(KB + (size_t)k * LDN + col);
+                        if (!isfinite(kv.x) || !isfinite(kv.y)) st |= DPILQR_ST_NONFINITE;
+                        *reinterpret_cast<double2 *>(Kt + 2 * e) = kv;
+                    }
+                } else {
+                    for (int e = tid - first; e < m_real * n_real; e += nw) {
+                        const int k = e / n_real, col = e - k * n_real;
+                        const double kv = KB[(size_t)k * LDN + col];
+                        if (!isfinite(kv)) st |= DPILQR_ST_NONFINITE;
+                        Kt[e] = kv;
+                    }
+                }
+            }
+        }
         // ---- phase E: pq = Q_ux^T d and z = Q_uu d + Q_u (before Q_ux is overwritten), then Y = Q_uu K + 2 Q_ux
         for (int col = tid; col < n + m; col += nthr) {
             if (col < n) {
