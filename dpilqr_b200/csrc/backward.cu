@@ -42,6 +42,13 @@ namespace dpilqr {
 #define DPILQR_UPPER_INVERSE 1
 #endif
 constexpr bool kUpperInverse = DPILQR_UPPER_INVERSE != 0;
+// Share of the column tiles of Q_ux = S A computed by the Q_xx warps (behind their blocks) instead of the LU group's
+// update warps: two fifths balance the two groups of the LU window for ten drones (LU 18.6 k -> 16.3 k cycles, Q_xx
+// group 16.7 k -> 17.9 k; -DDPILQR_QUX_SHARE_GROUP2_PCT=0: all on the update warps, as in round 1).
+#ifndef DPILQR_QUX_SHARE_GROUP2_PCT
+#define DPILQR_QUX_SHARE_GROUP2_PCT 40
+#endif
+__host__ __device__ constexpr int qux_tiles_group2(int nt) { return nt * DPILQR_QUX_SHARE_GROUP2_PCT / 100; }
 
 template <int S>
 struct TileSize {
@@ -511,6 +518,35 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         // the twelve warps of the other sub-partitions compute Q_xx.  Otherwise: first 256 threads / the rest.
         constexpr int kLuThreads = USE_MMA ? 128 : kSolveThreads;
         const bool lu_group = tid < kLuThreads;
+        // one 8-column tile of Q_ux = S A on the tensor path: the A_j operand is shared by the MT row tiles, whose
+        // independent accumulator chains keep the tensor pipe busy
+        auto qux_tile = [&](int ct) {
+            if constexpr (MMA_A) {
+                constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
+                constexpr int MT = M / 8;
+                const int fr = lane >> 2, fc = lane & 3;
+                const double *Ssm = KB;
+                const int col = 8 * ct + fr;
+                const int bj = col / S, cc = col - bj * S;
+                const int j0 = (8 * ct) / S, j1 = (8 * ct + 7) / S;
+                double2 acc[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) acc[mt] = make_double2(0.0, 0.0);
+                for (int ja = j0; ja <= j1; ++ja) {
+                    const double *sp = Ssm + (size_t)fr * LD + ja * S + fc;
+                    const double *ap = sA + ja * SAS + fc * S + cc;
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk) {
+                        const double bv = (ja == bj) ? ap[4 * kk * S] : 0.0;
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) dmma_m8n8k4(acc[mt].x, acc[mt].y, sp[(size_t)8 * mt * LD + 4 * kk], bv);
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    *reinterpret_cast<double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * ct + 2 * fc) = acc[mt];
+            }
+        };
         const bool idle_group = USE_MMA && !lu_group && ((warp & 3) == 0);  // shares the scheduler of the panel warp
         if (lu_group) {
             // ================= group 1: phase C, LU with implicit partial pivoting =================
@@ -519,33 +555,10 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 // Q_ux = S A (L_ux == 0, cost.py:91): only phase D needs it, so it runs in the shadow of the LU: the three
                 // update warps of the LU group do it while warp 0 factorises the first panel (they have nothing else to do
                 // until then); the warps that share the panel warp's scheduler stay parked
-                constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
-                constexpr int NT = N / 8, MT = M / 8;
-                const int fr = lane >> 2, fc = lane & 3;
-                const double *Ssm = KB;
-                // a warp takes whole column tiles: the A_j operand is shared by the MT row tiles, whose independent
-                // accumulator chains keep the tensor pipe busy -- these warps are due back at the first trailing update
-                for (int ct = (gt >> 5) - 1; ct < NT && (gt >> 5) >= 1; ct += 3) {
-                    const int col = 8 * ct + fr;
-                    const int bj = col / S, cc = col - bj * S;
-                    const int j0 = (8 * ct) / S, j1 = (8 * ct + 7) / S;
-                    double2 acc[MT];
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) acc[mt] = make_double2(0.0, 0.0);
-                    for (int ja = j0; ja <= j1; ++ja) {
-                        const double *sp = Ssm + (size_t)fr * LD + ja * S + fc;
-                        const double *ap = sA + ja * SAS + fc * S + cc;
-#pragma unroll
-                        for (int kk = 0; kk < 3; ++kk) {
-                            const double bv = (ja == bj) ? ap[4 * kk * S] : 0.0;
-#pragma unroll
-                            for (int mt = 0; mt < MT; ++mt) dmma_m8n8k4(acc[mt].x, acc[mt].y, sp[(size_t)8 * mt * LD + 4 * kk], bv);
-                        }
-                    }
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-                        *reinterpret_cast<double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * ct + 2 * fc) = acc[mt];
-                }
+                // a warp takes whole column tiles -- these warps are due back at the first trailing update; the last
+                // qux_tiles_group2(NT) column tiles go to the Q_xx warps instead, behind their blocks
+                constexpr int NT = (AT * S) / 8;
+                for (int ct = (gt >> 5) - 1; ct < NT - qux_tiles_group2(NT) && (gt >> 5) >= 1; ct += 3) qux_tile(ct);
             }
             if constexpr (USE_MMA)
                 lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid < 32) ? tacc + 24 : nullptr);
@@ -658,6 +671,10 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                                 *reinterpret_cast<double2 *>(Pblk + r * S + cc) = make_double2(out[0], out[1]);
                             }
                         }
+                }
+                {
+                    constexpr int NT = (AT * S) / 8;
+                    for (int ct = NT - qux_tiles_group2(NT) + (gt >> 5); ct < NT; ct += gn >> 5) qux_tile(ct);
                 }
             } else {
             for (int blk0 = (p.debug_mode & 16) ? nblk : 0; blk0 < nblk; blk0 += blocks_per_round) {
