@@ -42,11 +42,23 @@ namespace dpilqr {
 #define DPILQR_UPPER_INVERSE 1
 #endif
 constexpr bool kUpperInverse = DPILQR_UPPER_INVERSE != 0;
+#ifndef DPILQR_PACK_IN_LU
+#define DPILQR_PACK_IN_LU 0
+#endif
+#ifndef DPILQR_MERGE_E
+#define DPILQR_MERGE_E 1
+#endif
+#ifndef DPILQR_K_FROM_D
+#define DPILQR_K_FROM_D 1
+#endif
+#ifndef DPILQR_F_BALANCE
+#define DPILQR_F_BALANCE 1
+#endif
 // Share of the column tiles of Q_ux = S A computed by the Q_xx warps (behind their blocks) instead of the LU group's
 // update warps: two fifths balance the two groups of the LU window for ten drones (LU 18.6 k -> 16.3 k cycles, Q_xx
 // group 16.7 k -> 17.9 k; -DDPILQR_QUX_SHARE_GROUP2_PCT=0: all on the update warps, as in round 1).
 #ifndef DPILQR_QUX_SHARE_GROUP2_PCT
-#define DPILQR_QUX_SHARE_GROUP2_PCT 40
+#define DPILQR_QUX_SHARE_GROUP2_PCT 54
 #endif
 __host__ __device__ constexpr int qux_tiles_group2(int nt) { return nt * DPILQR_QUX_SHARE_GROUP2_PCT / 100; }
 
@@ -134,6 +146,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     constexpr int SAS = S * S + 2, SBS = S * C + 2;
     constexpr bool USE_MMA = (AT > 0) && (S % 2 == 0) && ((AT * S) % 8 == 0) && ((AT * C) % 8 == 0);
     constexpr bool MMA_A = USE_MMA && S == 12 && C == 4 && AT % 2 == 0;  // phase A on the tensor path
+    constexpr bool kMergeE = USE_MMA && !GLOBAL && (AT * S) / 8 < 16 && (AT * S) % 8 == 0 && kUpperInverse && DPILQR_MERGE_E;  // phase E in one piece, see there
+    constexpr bool kKFromD = kMergeE && DPILQR_K_FROM_D;  // K[t], d[t] leave for HBM from the fragments of phase D
     const int LDQ = m + 4;
     const int LDW = backward_ldw(m);  // row stride of the LU work matrix
     const int LDF = backward_ldf(m);  // row stride of the packed factors
@@ -337,6 +351,64 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     if (p.debug_mode & 32) lu_experiment(27);
     if (timing) tmark = clock64();
 #pragma unroll 1
+        // Pack the factors in pivot order so that the substitutions read contiguous memory, and invert the 8x8 diagonal
+        // blocks.  gn threads (gt = 0..gn-1) that synchronise with sync().
+        auto pack_factors = [&](int gt, int gn, auto sync) {
+        for (int e = gt; e < m * m; e += gn) {
+            const int k = e / m, x2 = e - k * m;
+            const double v = W[order[x2] * LDW + k];
+            if (x2 > k) Lp[k * LDF + x2] = v;   // l(x2, k)
+            else Up[k * LDF + x2] = v;          // u(x2, k): column k, row x2 <= k
+            if (x2 == k) {
+                if (v == 0.0) st |= DPILQR_ST_SINGULAR;  // exact zero pivot: dgesv's info > 0 (a NaN pivot is not: np.linalg.solve returns NaN)
+                rdiag[k] = __drcp_rn(v);
+            }
+        }
+        if constexpr (USE_MMA) {
+            // The blocked forward solve of phase D applies the 8x8 diagonal blocks of the unit lower factor (well
+            // conditioned: |l| <= 1) as explicit inverses on the tensor path: invert them here, in place.  One
+            // thread per (block, column of the inverse).
+            constexpr int M = AT * C, NB = M / 8;
+            sync();
+            const int bb = (gt & 63) >> 3, j = gt & 7;
+            double x[8];
+            const bool busy = gt < NB * 8;
+            const bool busy_u = kUpperInverse && gt >= 64 && gt < 64 + NB * 8;  // (NB <= 8: the two groups are disjoint)
+            if (busy) {
+                const double *F = Lp + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = l(rr, c) of this block
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {  // unit lower: solve L x = e_j by forward substitution
+                    double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int c = 0; c < i; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
+                    x[i] = acc;
+                }
+            } else if (busy_u) {
+                const double *F = Up + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = u(rr, c), rr <= c
+#pragma unroll
+                for (int i = 7; i >= 0; --i) {  // upper: solve U x = e_j by back substitution (x_i = 0 for i > j)
+                    // row i scaled by 1 / u_ii beforehand: the chain from x_7 down to x_0 is then one FMA per row (a
+                    // dependent FP64 operation costs some 50 cycles) instead of an FMA and a multiplication
+                    const double ri = rdiag[8 * bb + i];
+                    double acc = (i == j) ? ri : 0.0;
+#pragma unroll
+                    for (int c = i + 1; c < 8; ++c) acc = fma(-(F[c * LDF + i] * ri), x[c], acc);
+                    x[i] = (i <= j) ? acc : 0.0;
+                }
+            }
+            sync();
+            if (busy) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Lp[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j), same transposed layout
+            } else if (busy_u) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Up[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j); zero below the diagonal
+            }
+        }
+        };
+        // The LU group finishes ahead of the Q_xx warps in the shared-memory tensor-path kernels: it packs its factors
+        // there, off the critical path (with the factors in the L2 scratch 128 threads would be too few to hide its latency).
+        constexpr bool kPackInLu = USE_MMA && !GLOBAL && DPILQR_PACK_IN_LU;
     for (int t = T - 1; t >= 0; --t) {
         if ((p.debug_mode & 256) && t == T - 1) lu_experiment(28);
         {
@@ -345,6 +417,55 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         // both sides of the diagonal, and phases B and F round the two triangles independently: the antisymmetric
         // residue is not damped by the recursion (it propagates with the open-loop A^T . A and grew by about 12 % per
         // time step on Quadcopter12D, costing two to three digits of K and d at t = 0).
+        if constexpr (kMergeE) {
+            // Phase E in one piece: the lower half of the CTA finishes the step before -- p <- Q_x + K^T z + Q_ux^T d, whose
+            // first reader is phase A (K, z, pq and Q_x are intact until then) -- while the upper half symmetrises and
+            // sets the regularised diagonal up.  A dependent FP64 operation costs 50 to 70 cycles here, so both are
+            // built for short chains: two threads per entry of p with four partial sums of five terms each; every
+            // symmetrisation pair loaded before the first is stored.
+            constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
+            constexpr int NPAIR = AT * (S * (S - 1) / 2), ITER = (NPAIR + 255) / 256;
+            static_assert(2 * N <= 256 && N <= 256, "p update: two threads per column in the lower half of the CTA");
+            if (tid < 256) {
+                const int col = min(tid >> 1, N - 1), h = tid & 1;  // (the surplus lanes of the last warp shuffle along)
+                if (t < T - 1) {
+                    const double *kp = KB + (size_t)(4 * h) * LD + col;
+                    const double *zp = zv + 4 * h;
+                    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int i = 0; i < M / 8; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) a4[c] = fma(kp[(size_t)(8 * i + c) * LD], zp[8 * i + c], a4[c]);
+                    double sum = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    const double pnew = Qx[col] + sum + pq[col];
+                    if (!isfinite(pnew)) st |= DPILQR_ST_NONFINITE;
+                    if (h == 0 && tid < 2 * N) pvec[col] = pnew;
+                }
+            } else {
+                const int u = tid - 256;
+                if (u < N) {  // P + mu I for phase A (control.py:134-135): P itself stays as it is
+                    const int i = u / S, r = u - i * S;
+                    colbuf[u] = Pb[(size_t)blk_index(i, i) * PBS + r * S + r] + scal[0];
+                }
+                double *lo[ITER], *up[ITER];
+                double v[ITER];
+#pragma unroll
+                for (int it = 0; it < ITER; ++it) {
+                    const int q = min(u + 256 * it, NPAIR - 1);  // (the surplus threads compute the last pair and drop it)
+                    const int i = q / (S * (S - 1) / 2);
+                    int w = q - i * (S * (S - 1) / 2), r = 0;
+                    while (w >= S - 1 - r) { w -= S - 1 - r; ++r; }
+                    const int cc = r + 1 + w;
+                    double *blk = Pb + (size_t)blk_index(i, i) * PBS;
+                    up[it] = blk + r * S + cc, lo[it] = blk + cc * S + r;
+                    v[it] = 0.5 * (*up[it] + *lo[it]);
+                }
+#pragma unroll
+                for (int it = 0; it < ITER; ++it)
+                    if (u + 256 * it < NPAIR) *up[it] = v[it], *lo[it] = v[it];
+            }
+        } else {
         {
             for (int k = tid; k < a * S * S; k += nthr) {  // one item per entry, the upper ones act (constant divisors only)
                 const int i = k / (S * S), e = k - i * (S * S);
@@ -359,12 +480,23 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         }
         // Regularise P in place for phase A (P + mu I, control.py:134-135); the plain diagonal waits in pq (free until
         // phase E) and is put back before phase B, which needs the unregularised P.
+        // The tensor-path form of phase A leaves P alone and takes the regularised diagonal from a side buffer (the LU's
+        // look-ahead buffer, free outside the factorisation): nothing to restore, no barrier in front of phase B.
+        if constexpr (MMA_A) {
+            for (int k = tid; k < n; k += nthr) {
+                const int i = k / S, r = k - i * S;
+                colbuf[k] = Pb[(size_t)blk_index(i, i) * PBS + r * S + r] + scal[0];
+            }
+        }
+        }
+        if constexpr (!MMA_A) {
         for (int k = (p.debug_mode & 8) ? n : tid; k < n; k += nthr) {
             const int i = k / S, r = k - i * S;
             double *pd = Pb + (size_t)blk_index(i, i) * PBS + r * S + r;
             const double v = *pd;
             pq[k] = v;
             *pd = v + scal[0];
+        }
         }
         }
         tick(9);
@@ -395,8 +527,11 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     const int ag = 2 * pr + ks / 3;    // agent whose rows of P this k-step covers
                     const int rr = 4 * (ks % 3) + fc;  // row inside that agent's block
                     const double av = ((fr >> 2) == ks / 3) ? sB[ag * SBS + rr * C + (fr & 3)] : 0.0;
-                    const double bv = (ag <= bj) ? Pb[(size_t)blk_index(ag, bj) * PBS + rr * S + cc]
-                                                 : Pb[(size_t)blk_index(bj, ag) * PBS + cc * S + rr];
+                    // (diagonal entries come regularised from their side buffer: P itself stays as it is)
+                    // (an index into the shared-memory array, not a pointer: the select must not turn the load generic)
+                    int src = (int)SM.Pb + ((ag <= bj) ? blk_index(ag, bj) * PBS + rr * S + cc : blk_index(bj, ag) * PBS + cc * S + rr);
+                    if (ag == bj && rr == cc) src = (int)SM.keys + col;
+                    const double bv = smem[src];
                     if (ks < 3) dmma_m8n8k4(c0, c1, av, bv);
                     else dmma_m8n8k4(e0, e1, av, bv);
                 }
@@ -417,18 +552,20 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 {
                     // Q_uu tile: rows 8 mt.. (agents 2 mt, 2 mt + 1), columns 8 nt.. (agents 2 nt, 2 nt + 1)
                     const int mt = q / MT, nt = q - mt * MT;
-                    double c0 = 0.0, c1 = 0.0;
+                    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // one accumulator chain per agent of the column pair
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int ja = 2 * nt + e;
-                        const double *sp = Ssm + (size_t)(8 * mt + fr) * LD + ja * S + fc;
-                        const double *bp = sB + ja * SBS + fc * C + (fr & 3);
+                    for (int kk = 0; kk < 3; ++kk) {
 #pragma unroll
-                        for (int kk = 0; kk < 3; ++kk) {
+                        for (int e = 0; e < 2; ++e) {
+                            const int ja = 2 * nt + e;
+                            const double *sp = Ssm + (size_t)(8 * mt + fr) * LD + ja * S + fc;
+                            const double *bp = sB + ja * SBS + fc * C + (fr & 3);
                             const double bv = ((fr >> 2) == e) ? bp[4 * kk * C] : 0.0;
-                            dmma_m8n8k4(c0, c1, sp[4 * kk], bv);
+                            if (e == 0) dmma_m8n8k4(c0, c1, sp[4 * kk], bv);
+                            else dmma_m8n8k4(e0, e1, sp[4 * kk], bv);
                         }
                     }
+                    c0 += e0, c1 += e1;
                     const int row = 8 * mt + fr, colq = 8 * nt + 2 * fc;
                     const int ir = row / C, g = row - ir * C, ic = colq / C, g2 = colq - ic * C;
                     if (ir == ic) {  // L_uu of the reference cost, w (R + R^T) (cost.py:85-93)
@@ -563,6 +700,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             if constexpr (USE_MMA)
                 lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid < 32) ? tacc + 24 : nullptr);
             else lu_lookahead<(AT > 0 ? AT * C : 0)>(W, colbuf, rinvbuf, prbuf, order, m, gt);
+            if constexpr (kPackInLu) pack_factors(gt, kLuThreads, [] { named_barrier(1, kLuThreads); });
             tick(2);
             if constexpr (USE_MMA && TIMED) {  // timing experiment: a second, warm pass over the same code
                 if (p.debug_mode & 4) lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, nullptr);
@@ -572,11 +710,13 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             const int gt = USE_MMA ? ((((warp >> 2) - 1) * 3 + (warp & 3) - 1) << 5) + lane : tid - kSolveThreads;
             const int gn = USE_MMA ? 288 : nthr - kLuThreads;
             const int blocks_per_round = gn / S;
+            if constexpr (!MMA_A) {
             for (int k = gt; k < n; k += gn) {  // the unregularised diagonal of P comes back
                 const int i = k / S, r = k - i * S;
                 Pb[(size_t)blk_index(i, i) * PBS + r * S + r] = pq[k];
             }
             named_barrier(2, gn);
+            }
             tick(3);
             if constexpr (MMA_A) {
                 // Tensor-path form: every warp owns whole blocks.  V = P_ij A_j in four 8x8 accumulator tiles (the
@@ -673,8 +813,9 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                         }
                 }
                 {
-                    constexpr int NT = (AT * S) / 8;
-                    for (int ct = NT - qux_tiles_group2(NT) + (gt >> 5); ct < NT; ct += gn >> 5) qux_tile(ct);
+                    // the column tiles continue the round robin of the blocks: the warps that had one block fewer go first
+                    constexpr int NT = (AT * S) / 8, NW = 9, SHARE = qux_tiles_group2(NT);
+                    for (int u = nblk + ((gt >> 5) + NW - nblk % NW) % NW; u < nblk + SHARE; u += NW) qux_tile(NT - SHARE + u - nblk);
                 }
             } else {
             for (int blk0 = (p.debug_mode & 16) ? nblk : 0; blk0 < nblk; blk0 += blocks_per_round) {
@@ -752,55 +893,9 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         tick(3);
         {
             DPILQR_PHASE_IDS
-        // ---- pack the factors in pivot order so the substitutions read contiguous memory (all threads)
-        for (int e = tid; e < m * m; e += nthr) {
-            const int k = e / m, x2 = e - k * m;
-            const double v = W[order[x2] * LDW + k];
-            if (x2 > k) Lp[k * LDF + x2] = v;   // l(x2, k)
-            else Up[k * LDF + x2] = v;          // u(x2, k): column k, row x2 <= k
-            if (x2 == k) {
-                if (v == 0.0) st |= DPILQR_ST_SINGULAR;  // exact zero pivot: dgesv's info > 0 (a NaN pivot is not: np.linalg.solve returns NaN)
-                rdiag[k] = __drcp_rn(v);
-            }
-        }
-        if constexpr (USE_MMA) {
-            // The blocked forward solve of phase D applies the 8x8 diagonal blocks of the unit lower factor (well
-            // conditioned: |l| <= 1) as explicit inverses on the tensor path: invert them here, in place.  One
-            // thread per (block, column of the inverse).
-            constexpr int M = AT * C, NB = M / 8;
-            __syncthreads();
-            const int bb = (tid & 63) >> 3, j = tid & 7;
-            double x[8];
-            const bool busy = tid < NB * 8;
-            const bool busy_u = kUpperInverse && tid >= 64 && tid < 64 + NB * 8;  // (NB <= 8: the two groups are disjoint)
-            if (busy) {
-                const double *F = Lp + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = l(rr, c) of this block
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {  // unit lower: solve L x = e_j by forward substitution
-                    double acc = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int c = 0; c < i; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
-                    x[i] = acc;
-                }
-            } else if (busy_u) {
-                const double *F = Up + (8 * bb) * LDF + 8 * bb;  // F[c * LDF + rr] = u(rr, c), rr <= c
-#pragma unroll
-                for (int i = 7; i >= 0; --i) {  // upper: solve U x = e_j by back substitution (x_i = 0 for i > j)
-                    double acc = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int c = i + 1; c < 8; ++c) acc = fma(-F[c * LDF + i], x[c], acc);
-                    x[i] = (i <= j) ? acc * rdiag[8 * bb + i] : 0.0;
-                }
-            }
-            __syncthreads();
-            if (busy) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) Lp[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j), same transposed layout
-            } else if (busy_u) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) Up[(8 * bb + j) * LDF + 8 * bb + i] = x[i];  // inverse(i, j); zero below the diagonal
-            }
-        }
+        // ---- pack the factors in pivot order so the substitutions read contiguous memory (all threads; the
+        // shared-memory tensor-path kernels have done it in the LU group, behind the factorisation)
+        if constexpr (!kPackInLu) pack_factors(tid, nthr, [] { __syncthreads(); });
         }
         __syncthreads();
         tick(5);
@@ -872,6 +967,21 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                         __syncwarp();
                         xc[blk] = make_double2(d0, d1);
                         *reinterpret_cast<double2 *>(Xc + (size_t)(8 * blk + fr) * LDN + 2 * fc) = xc[blk];
+                        if constexpr (kKFromD) {
+                            // these rows of K[t] (and of d[t], right-hand side n) are final: they leave for HBM straight
+                            // from the accumulator fragment, 64 contiguous bytes per row of the tile
+                            const int row = 8 * blk + fr, col = 8 * nt + 2 * fc;
+                            if (row < m_real) {
+                                if (col < n_real) {  // (n_real is even: the pair stays inside the row)
+                                    if (!isfinite(d0) || !isfinite(d1)) st |= DPILQR_ST_NONFINITE;
+                                    double *kp = p.K + (((int64_t)problem() * T + t) * m_real + row) * n_real + col;
+                                    if ((reinterpret_cast<uintptr_t>(p.K) & 15) == 0) *reinterpret_cast<double2 *>(kp) = xc[blk];
+                                    else kp[0] = d0, kp[1] = d1;
+                                } else if (col == AT * S) {
+                                    p.d[((int64_t)problem() * T + t) * m_real + row] = d0;
+                                }
+                            }
+                        }
                     } else if (lane < 8) {
                         double x[8];
 #pragma unroll
@@ -984,6 +1094,99 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         }
         __syncthreads();
         tick(10);
+        if constexpr (kMergeE) {
+            DPILQR_PHASE_IDS
+            // ---- phase E in one piece (shared-memory tensor-path kernels, at most 15 column tiles): a warp owns a whole
+            // column tile of Q_ux -- nobody else reads or writes those columns -- so pq = Q_ux^T d for its eight columns
+            // comes first and Y = Q_uu K + 2 Q_ux then goes over the tile in place, with no block barrier between the
+            // two; the spare last warp computes z = Q_uu d + Q_u.  d is read where phase D left it (column n of the K
+            // buffer); K[t] and d[t] went out to HBM from phase D.  Same partial sums and the same order of additions as the vector phase of
+            // the other kernels.
+            constexpr int N = AT * S, M = AT * C, LD = backward_ldn(N);
+            constexpr int MT = M / 8, NT = N / 8, KS = M / 4;
+            static_assert(NT < 16, "phase E: the last warp is spare");
+            // instrumented build: cycles from the start of the phase to the end of every warp's own work (slots 32 + warp)
+            // and to the end of its pq (slots 48 + warp) of CTA 0; the timing buffer has 64 entries
+            const bool etime = TIMED && p.timing != nullptr && blockIdx.x == 0;
+            const long long e_start = etime ? clock64() : 0;
+            if (t > 0) prefetch_record(t - 1, nthr - 1);
+            if constexpr (!kKFromD) {
+                // K[t] streams out to HBM (K stays in shared memory until phase A of the next step reuses the buffer)
+                double *Kt = p.K + ((int64_t)problem() * T + t) * m_real * n_real;
+                if ((n_real & 1) == 0 && (reinterpret_cast<uintptr_t>(p.K) & 15) == 0) {  // coalesced, two entries per access
+                    for (int e = tid; e < (m_real * n_real) >> 1; e += nthr) {
+                        const int k = (2 * e) / n_real, col = 2 * e - k * n_real;
+                        const double2 kv = *reinterpret_cast<const double2 *>(KB + (size_t)k * LD + col);
+                        if (!isfinite(kv.x) || !isfinite(kv.y)) st |= DPILQR_ST_NONFINITE;
+                        *reinterpret_cast<double2 *>(Kt + 2 * e) = kv;
+                    }
+                } else {
+                    for (int e = tid; e < m_real * n_real; e += nthr) {
+                        const int k = e / n_real, col = e - k * n_real;
+                        const double kv = KB[(size_t)k * LD + col];
+                        if (!isfinite(kv)) st |= DPILQR_ST_NONFINITE;
+                        Kt[e] = kv;
+                    }
+                }
+                for (int k = tid; k < m_real; k += nthr) p.d[((int64_t)problem() * T + t) * m_real + k] = KB[(size_t)k * LD + N];
+            }
+            const int fr = lane >> 2, fc = lane & 3;  // fragment coordinates
+            if (warp == nwarp - 1) {
+                // z = Q_uu d + Q_u (phase F needs it for p).  Plain FMAs spread like pq: lane (fr, fc) sums the terms
+                // k = fc (mod 4) of row 8 mt + fr, two shuffles add the four partial sums.  (Anything more on this warp
+                // holds the phase up: its FMAs queue behind the tensor instructions of the three column-tile warps
+                // that share its scheduler's FP64 pipe.)
+                double q[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) q[mt] = 0.0;
+                const double *ap = QUU + fr * LDQ + fc;
+                const double *dp = KB + (size_t)fc * LD + N;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const double dk = dp[(size_t)4 * ks * LD];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) q[mt] = fma(ap[8 * mt * LDQ + 4 * ks], dk, q[mt]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    q[mt] += __shfl_xor_sync(0xffffffffu, q[mt], 1);
+                    q[mt] += __shfl_xor_sync(0xffffffffu, q[mt], 2);
+                    if (fc == 0) zv[8 * mt + fr] = q[mt] + Qu[8 * mt + fr];
+                }
+            }
+            for (int nt = warp; nt < NT; nt += nwarp) {
+                // pq for columns 8 nt .. 8 nt + 7: lane (fr, fc) sums the rows k = fc (mod 4) of column 8 nt + fr, one
+                // term per k-step of the tile product below -- a chain of ten dependent FMAs (some 50 cycles each) that
+                // would hold the warp's tensor instructions up for a thousand cycles if it came first
+                const double *qp = QUX + (size_t)fc * LD + 8 * nt + fr;
+                const double *dp = KB + (size_t)fc * LD + N;
+                double q = 0.0;
+                double2 acc[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const double2 y0 = *reinterpret_cast<const double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * nt + 2 * fc);
+                    acc[mt] = make_double2(2.0 * y0.x, 2.0 * y0.y);
+                }
+                const double *ap = QUU + fr * LDQ + fc;
+                const double *bp = KB + (size_t)fc * LD + 8 * nt + fr;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const double bv = bp[(size_t)4 * ks * LD];
+                    q = fma(qp[(size_t)4 * ks * LD], dp[(size_t)4 * ks * LD], q);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) dmma_m8n8k4(acc[mt].x, acc[mt].y, ap[8 * mt * LDQ + 4 * ks], bv);
+                }
+                q += __shfl_xor_sync(0xffffffffu, q, 1);
+                q += __shfl_xor_sync(0xffffffffu, q, 2);
+                if (fc == 0) pq[8 * nt + fr] = q;
+                if (etime && lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(p.timing) + 48 + warp, (unsigned long long)(clock64() - e_start));
+                __syncwarp();  // every lane has read the column tile of Q_ux: overwrite it with Y
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    *reinterpret_cast<double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * nt + 2 * fc) = acc[mt];
+            }
+            if (etime && lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(p.timing) + 32 + warp, (unsigned long long)(clock64() - e_start));
+        } else {
         {
             DPILQR_PHASE_IDS
         for (int k = tid; k < m; k += nthr) {
@@ -1081,6 +1284,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             }
         }
         }
+        }
         __syncthreads();
         tick(7);
 
@@ -1093,10 +1297,6 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             constexpr int NT = N / 8, KS = M / 4;
             constexpr int NTILES = NT * (NT + 1) / 2;
             const int fr = lane >> 2, fc = lane & 3;
-            const int q0 = (NTILES * warp) / nwarp, q1 = (NTILES * (warp + 1)) / nwarp;
-            int ti = 0, rowstart = 0;  // decode q0 -> (ti, tj) in the row-major upper triangle of tiles
-            while (q0 >= rowstart + (NT - ti)) { rowstart += NT - ti; ++ti; }
-            int tj = ti + (q0 - rowstart);
             auto add_tile = [&](int tr, int tc, double c0, double c1) {  // P tile (tr, tc) += 1/2 (c0, c1)
                 const int row = 8 * tr + fr, col = 8 * tc + 2 * fc;
                 const int bi = row / S, bj = col / S;  // S is even here, so the pair (col, col+1) shares a block
@@ -1113,6 +1313,14 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     }
                 }
             };
+            // warps w, w+4, w+8, w+12 share a scheduler (and its FP64 pipe): when the tile count does not divide by the warp
+            // count, every other slot has one tile more -- swap the slots of neighbouring warps in every other group of
+            // four, so that each scheduler gets as many long slots as short ones
+            const int slot = DPILQR_F_BALANCE ? (warp ^ ((warp >> 2) & 1)) : warp;
+            const int q0 = (NTILES * slot) / nwarp, q1 = (NTILES * (slot + 1)) / nwarp;
+            int ti = 0, rowstart = 0;  // decode q0 -> (ti, tj) in the row-major upper triangle of tiles
+            while (q0 >= rowstart + (NT - ti)) { rowstart += NT - ti; ++ti; }
+            int tj = ti + (q0 - rowstart);
             for (int q = q0; q < q1;) {
                 // Two neighbouring tiles of a tile row share the row's operand fragments (K^T and Y^T of rows 8 ti..):
                 // six shared-memory loads for four tensor instructions instead of eight, four independent chains.
@@ -1184,6 +1392,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     }
             }
         }
+        if constexpr (!kMergeE) {
         for (int col = tid; col < n; col += nthr) {
             double a4[4] = {0.0, 0.0, 0.0, 0.0};
             int k = 0;
@@ -1196,6 +1405,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             const double pnew = Qx[col] + acc + pq[col];
             if (!isfinite(pnew)) st |= DPILQR_ST_NONFINITE;
             pvec[col] = pnew;
+        }
         }
         }
         __syncthreads();

@@ -29,7 +29,7 @@ for rep in range(12):
     torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
 print(f"product kernel: best of 12 launches {best:.3f} ms for {B} problems = {best * 1e-3 * 1.965e9 / 50:.0f} cycles/step at 1965 MHz")
-buf = torch.zeros(32, dtype=torch.int64, device="cuda")
+buf = torch.zeros(64, dtype=torch.int64, device="cuda")
 _native.lib().dpilqr_debug_backward_timing(ctypes.c_void_p(buf.data_ptr()))
 tbest = 1e9
 for rep in range(6):
@@ -50,4 +50,8 @@ print(f"  group2 phaseB {c[14] / 50:10.0f} cycles/step; total {tot / 50:.0f} cyc
 print(f"  group 2 detail: restore+barrier {c[15] / 50:.0f}  Q_xx blocks {c[16] / 50:.0f}  Q_ux tiles {c[14] / 50:.0f} cycles/step")
 print(f"  LU detail: first panel {c[24] / 50:.0f}  U12+tiles+waits {c[25] / 50:.0f}  panels 1..4 {c[26] / 50:.0f} cycles/step")
 print(f"  LU experiment (debug modes 32/256/512): before the recursion {c[27]}, top of the first step {c[28]}, after phase A of the second step {c[29]} cycles")
+if c[32:48].any():
+    nl = 6 * 50  # instrumented launches x steps
+    print("  phase E per warp, cycles/step to the end of its own work:", " ".join(f"{v / nl:.0f}" for v in c[32:48]))
+    print("  phase E per warp, cycles/step to the end of its pq:      ", " ".join(f"{v / nl:.0f}" for v in c[48:64]))
 _native.lib().dpilqr_debug_backward_timing(None)
