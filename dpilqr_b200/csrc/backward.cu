@@ -51,6 +51,9 @@ constexpr bool kUpperInverse = DPILQR_UPPER_INVERSE != 0;
 #ifndef DPILQR_K_FROM_D
 #define DPILQR_K_FROM_D 1
 #endif
+#ifndef DPILQR_LU_ON_SCHED0
+#define DPILQR_LU_ON_SCHED0 1
+#endif
 #ifndef DPILQR_F_BALANCE
 #define DPILQR_F_BALANCE 1
 #endif
@@ -651,10 +654,16 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
         {
             DPILQR_PHASE_IDS
         // Two warp groups run side by side.  Tensor-path kernels split by scheduler: the warps of SM sub-partition 0
-        // (warp % 4 == 0) factorise Q_uu -- the panel warp is latency-bound and keeps its FP64 pipe to itself -- while
-        // the twelve warps of the other sub-partitions compute Q_xx.  Otherwise: first 256 threads / the rest.
+        // (warp % 4 == 0) factorise Q_uu -- the panel warp is latency-bound and shares its FP64 pipe with nothing but the
+        // trailing updates of its own group -- while the twelve warps of the other sub-partitions compute Q_xx and
+        // Q_ux.  Otherwise: first 256 threads / the rest.
         constexpr int kLuThreads = USE_MMA ? 128 : kSolveThreads;
-        const bool lu_group = tid < kLuThreads;
+        // (-DDPILQR_LU_ON_SCHED0=0: the earlier split -- warps 0..3 factorise, one per sub-partition, with the three update
+        // warps competing with nine Q_xx warps for the tensor pipes and the three other warps of the panel warp's
+        // sub-partition parked.  Measured, ten drones: LU group 15.2 k, Q_xx warps 16.5 k cycles per step, against 15.8 k
+        // and 14.8 k with the split by sub-partition; 12 drones 30.7 -> 24.8 us per problem.)
+        constexpr bool kLuSched0 = USE_MMA && DPILQR_LU_ON_SCHED0;
+        const bool lu_group = kLuSched0 ? ((warp & 3) == 0) : (tid < kLuThreads);
         // one 8-column tile of Q_ux = S A on the tensor path: the A_j operand is shared by the MT row tiles, whose
         // independent accumulator chains keep the tensor pipe busy
         auto qux_tile = [&](int ct) {
@@ -684,10 +693,10 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     *reinterpret_cast<double2 *>(QUX + (size_t)(8 * mt + fr) * LD + 8 * ct + 2 * fc) = acc[mt];
             }
         };
-        const bool idle_group = USE_MMA && !lu_group && ((warp & 3) == 0);  // shares the scheduler of the panel warp
+        const bool idle_group = USE_MMA && !kLuSched0 && !lu_group && ((warp & 3) == 0);  // shares the scheduler of the panel warp
         if (lu_group) {
             // ================= group 1: phase C, LU with implicit partial pivoting =================
-            const int gt = tid;
+            const int gt = kLuSched0 ? ((warp >> 2) << 5) + lane : tid;
             if constexpr (MMA_A) {
                 // Q_ux = S A (L_ux == 0, cost.py:91): only phase D needs it, so it runs in the shadow of the LU: the three
                 // update warps of the LU group do it while warp 0 factorises the first panel (they have nothing else to do
@@ -695,6 +704,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 // a warp takes whole column tiles -- these warps are due back at the first trailing update; the last
                 // qux_tiles_group2(NT) column tiles go to the Q_xx warps instead, behind their blocks
                 constexpr int NT = (AT * S) / 8;
+                if constexpr (!kLuSched0)
                 for (int ct = (gt >> 5) - 1; ct < NT - qux_tiles_group2(NT) && (gt >> 5) >= 1; ct += 3) qux_tile(ct);
             }
             if constexpr (USE_MMA)
@@ -707,8 +717,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             }
         } else if (!idle_group) {
             // ================= group 2: phase B, Q_xx = L_xx + A^T P A in place (upper blocks) =================
-            const int gt = USE_MMA ? ((((warp >> 2) - 1) * 3 + (warp & 3) - 1) << 5) + lane : tid - kSolveThreads;
-            const int gn = USE_MMA ? 288 : nthr - kLuThreads;
+            const int gt = kLuSched0 ? ((((warp >> 2) * 3 + (warp & 3) - 1) << 5) + lane) : USE_MMA ? ((((warp >> 2) - 1) * 3 + (warp & 3) - 1) << 5) + lane : tid - kSolveThreads;
+            const int gn = kLuSched0 ? 384 : USE_MMA ? 288 : nthr - kLuThreads;
             const int blocks_per_round = gn / S;
             if constexpr (!MMA_A) {
             for (int k = gt; k < n; k += gn) {  // the unregularised diagonal of P comes back
@@ -814,7 +824,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 }
                 {
                     // the column tiles continue the round robin of the blocks: the warps that had one block fewer go first
-                    constexpr int NT = (AT * S) / 8, NW = 9, SHARE = qux_tiles_group2(NT);
+                    constexpr int NT = (AT * S) / 8, NW = kLuSched0 ? 12 : 9, SHARE = kLuSched0 ? NT : qux_tiles_group2(NT);
                     for (int u = nblk + ((gt >> 5) + NW - nblk % NW) % NW; u < nblk + SHARE; u += NW) qux_tile(NT - SHARE + u - nblk);
                 }
             } else {
