@@ -54,6 +54,9 @@ constexpr bool kUpperInverse = DPILQR_UPPER_INVERSE != 0;
 #ifndef DPILQR_LU_ON_SCHED0
 #define DPILQR_LU_ON_SCHED0 1
 #endif
+#ifndef DPILQR_VEC_IN_WINDOW
+#define DPILQR_VEC_IN_WINDOW 1
+#endif
 #ifndef DPILQR_F_BALANCE
 #define DPILQR_F_BALANCE 1
 #endif
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
     constexpr bool USE_MMA = (AT > 0) && (S % 2 == 0) && ((AT * S) % 8 == 0) && ((AT * C) % 8 == 0);
     constexpr bool MMA_A = USE_MMA && S == 12 && C == 4 && AT % 2 == 0;  // phase A on the tensor path
     constexpr bool kMergeE = USE_MMA && !GLOBAL && (AT * S) / 8 < 16 && (AT * S) % 8 == 0 && kUpperInverse && DPILQR_MERGE_E;  // phase E in one piece, see there
+    constexpr bool kVecInWindow = MMA_A && DPILQR_LU_ON_SCHED0 && DPILQR_VEC_IN_WINDOW;  // Q_u, Q_x computed beside the LU, see there
     constexpr bool kKFromD = kMergeE && DPILQR_K_FROM_D;  // K[t], d[t] leave for HBM from the fragments of phase D
     const int LDQ = m + 4;
     const int LDW = backward_ldw(m);  // row stride of the LU work matrix
@@ -540,6 +544,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 }
                 *reinterpret_cast<double2 *>(Ssm + (size_t)(8 * pr + fr) * LD + 8 * ct + 2 * fc) = make_double2(c0 + e0, c1 + e1);
             }
+            if constexpr (!kVecInWindow) {
             for (int row = tid; row < m; row += nthr) {  // Q_u = L_u + B^T p
                 const int i = row / C, g = row - i * C;
                 const double *Bi = sB + i * SBS;
@@ -549,6 +554,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 const double qu = sLu[row] + acc;
                 Qu[row] = qu;
                 QUX[(size_t)row * LDN + n] = qu;  // Q_u rides along as right-hand side n
+            }
             }
             __syncthreads();
             for (int q = warp; q < MT * MT; q += nwarp) {  // Q_ux = S A follows in warp group 2, beside the LU
@@ -632,6 +638,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
             }
         }
         }
+        if constexpr (!kVecInWindow) {
         for (int col = tid; col < n; col += nthr) {
             const int j = col / S, sg = col - j * S;
             const double *Aj = sA + j * SAS;
@@ -639,6 +646,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
 #pragma unroll
             for (int r = 0; r < S; ++r) acc = fma(Aj[r * S + sg], pvec[j * S + r], acc);
             Qx[col] = sLx[col] + acc;
+        }
         }
         }
         if constexpr (TIMED) {
@@ -708,7 +716,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                 for (int ct = (gt >> 5) - 1; ct < NT - qux_tiles_group2(NT) && (gt >> 5) >= 1; ct += 3) qux_tile(ct);
             }
             if constexpr (USE_MMA)
-                lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid < 32) ? tacc + 24 : nullptr);
+                lu_blocked<AT * C, kLuThreads, TIMED>(W, order, reinterpret_cast<unsigned *>(colbuf), gt, (timing && tid < 32) ? tacc + 24 : nullptr,
+                                                        (timing && tid < 32) ? p.timing + 64 : nullptr);
             else lu_lookahead<(AT > 0 ? AT * C : 0)>(W, colbuf, rinvbuf, prbuf, order, m, gt);
             if constexpr (kPackInLu) pack_factors(gt, kLuThreads, [] { named_barrier(1, kLuThreads); });
             tick(2);
@@ -826,6 +835,35 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const BackwardParams p
                     // the column tiles continue the round robin of the blocks: the warps that had one block fewer go first
                     constexpr int NT = (AT * S) / 8, NW = kLuSched0 ? 12 : 9, SHARE = kLuSched0 ? NT : qux_tiles_group2(NT);
                     for (int u = nblk + ((gt >> 5) + NW - nblk % NW) % NW; u < nblk + SHARE; u += NW) qux_tile(NT - SHARE + u - nblk);
+                    if constexpr (kVecInWindow) {
+                        // Q_u = L_u + B^T p and Q_x = L_x + A^T p: nobody needs them before phase D, and each is a chain of
+                        // twelve dependent FMAs that used to trail phase A.  The last two warps of the group -- the
+                        // round robin gives them a unit less than most -- run up to three of those chains side by side.
+                        if ((gt >> 5) >= NW - 2) {
+                            const int u = gt - (NW - 2) * 32;  // 0..63
+                            for (int c0 = u; c0 < n; c0 += 128) {
+                                const int c1 = min(c0 + 64, n - 1), row = min(u, m - 1);
+                                const bool do_u = (c0 == u);  // first round: Q_u rides along
+                                const int j0 = c0 / S, j1 = c1 / S, iu = row / C;
+                                const double *A0 = sA + j0 * SAS + (c0 - j0 * S), *A1 = sA + j1 * SAS + (c1 - j1 * S);
+                                const double *Bu = sB + iu * SBS + (row - iu * C);
+                                double a0 = 0.0, a1 = 0.0, au = 0.0;
+#pragma unroll
+                                for (int r = 0; r < S; ++r) {
+                                    a0 = fma(A0[r * S], pvec[j0 * S + r], a0);
+                                    a1 = fma(A1[r * S], pvec[j1 * S + r], a1);
+                                    if (do_u) au = fma(Bu[r * C], pvec[iu * S + r], au);
+                                }
+                                Qx[c0] = sLx[c0] + a0;
+                                if (c0 + 64 < n) Qx[c1] = sLx[c1] + a1;
+                                if (do_u && u < m) {
+                                    const double qu = sLu[row] + au;
+                                    Qu[row] = qu;
+                                    QUX[(size_t)row * LDN + n] = qu;  // Q_u rides along as right-hand side n
+                                }
+                            }
+                        }
+                    }
                 }
             } else {
             for (int blk0 = (p.debug_mode & 16) ? nblk : 0; blk0 < nblk; blk0 += blocks_per_round) {

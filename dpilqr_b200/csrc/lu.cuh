@@ -199,9 +199,14 @@ __device__ __noinline__ void lu_lookahead(double *__restrict__ W, double *__rest
 //     of used rows masked to zero (rows never move).  The column tile of the NEXT panel is updated first so that
 //     warp 0 factorises panel p+1 while the other warps finish the update of panel p (look-ahead).
 // NT threads (gt = 0..NT-1) call this together; they synchronise on named barrier 1.
+#ifndef DPILQR_LU_LOOKAHEAD_FIRST
+#define DPILQR_LU_LOOKAHEAD_FIRST 1
+#endif
+constexpr bool kLookaheadFirst = DPILQR_LU_LOOKAHEAD_FIRST != 0;
+
 template <int M, int NT, bool TIMED = false>
 __device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restrict__ order, unsigned *__restrict__ donebuf, int gt,
-                                        long long *__restrict__ lt)
+                                        long long *__restrict__ lt, long long *__restrict__ gl = nullptr)
 {
     static_assert(M % 8 == 0 && M <= 64, "blocked LU: m must be a multiple of 8, at most 64");
     constexpr int LDW = backward_ldw(M);
@@ -225,6 +230,15 @@ __device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restri
             const long long now = clock64();
             if (lane == 0) lt[slot] += now - tm;
             tm = now;
+        }
+    };
+    // finer laps of warp 0 between the panels, into a global buffer (instrumented build): 0 barrier, 1 U12, 2 tile update
+    long long tg = 0;
+    auto glap = [&](int slot) {
+        if (TIMED && gl) {
+            const long long now = clock64();
+            if (lane == 0 && slot >= 0) atomicAdd(reinterpret_cast<unsigned long long *>(gl) + slot, (unsigned long long)(now - tg));
+            tg = now;
         }
     };
 #pragma unroll 1
@@ -296,7 +310,9 @@ __device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restri
             if (lane == 0) donebuf[2 * (p & 1)] = b0, donebuf[2 * (p & 1) + 1] = b1;
         }
         lap(p == 0 ? 0 : 2);
+        glap(-1);
         named_barrier(1, NT);  // panel p and every earlier trailing update are in shared memory
+        glap(0);
         if (p == NP - 1) break;
         // ---- trailing columns: every warp owns whole column tiles -- U12 of the eight columns by lanes 0..7 (the
         // 8-step forward substitution with the panel's unit-lower block on the pivot rows: 28 FMAs, a chain of 7),
@@ -304,6 +320,14 @@ __device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restri
         // straight on to factorise it (look-ahead): one barrier per panel.
         const unsigned dm0 = donebuf[2 * (p & 1)], dm1 = donebuf[2 * (p & 1) + 1];
         const int nct = NP - 1 - p;
+        // The look-ahead tile goes first and alone: a dependent chain -- warp 0's forward substitution and its two-deep
+        // tensor chains -- starves beside warps that issue independent FP64 work on the same sub-partition (measured:
+        // 8 -> 100 cycles per dependent FMA, 26 -> 400 per dependent tensor instruction next to three saturating warps).
+        // The other warps start their column tiles when warp 0 has finished its own (named barrier 3: warp 0 arrives,
+        // the others wait) and work in the shadow of the next panel.
+        if constexpr (kLookaheadFirst) {
+            if (warp != 0) asm volatile("bar.sync 3, %0;" ::"r"(NT) : "memory");
+        }
         for (int ct = warp; ct < nct; ct += (warp == 0 ? nct : NW - 1)) {
             const int col0 = c0 + 8 + 8 * ct;
             if (lane < 8) {
@@ -321,6 +345,7 @@ __device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restri
                 for (int i = 0; i < 8; ++i) W[order[c0 + i] * LDW + c] = u[i];
             }
             __syncwarp();
+            if (warp == 0) glap(1);
             double bv[2];  // rows of U12: the B operand of every row tile
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) bv[kk] = W[order[c0 + 4 * kk + (lane & 3)] * LDW + col0 + (lane >> 2)];
@@ -338,6 +363,10 @@ __device__ __forceinline__ void lu_blocked(double *__restrict__ W, int *__restri
                 *cptr = cv;
             }
             __syncwarp();
+            if (warp == 0) glap(2);
+            if constexpr (kLookaheadFirst) {
+                if (warp == 0) asm volatile("bar.arrive 3, %0;" ::"r"(NT) : "memory");
+            }
         }
         lap(1);
     }

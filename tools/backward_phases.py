@@ -29,7 +29,7 @@ for rep in range(12):
     torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
 print(f"product kernel: best of 12 launches {best:.3f} ms for {B} problems = {best * 1e-3 * 1.965e9 / 50:.0f} cycles/step at 1965 MHz")
-buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+buf = torch.zeros(96, dtype=torch.int64, device="cuda")
 _native.lib().dpilqr_debug_backward_timing(ctypes.c_void_p(buf.data_ptr()))
 tbest = 1e9
 for rep in range(6):
@@ -54,4 +54,7 @@ if c[32:48].any():
     nl = 6 * 50  # instrumented launches x steps
     print("  phase E per warp, cycles/step to the end of its own work:", " ".join(f"{v / nl:.0f}" for v in c[32:48]))
     print("  phase E per warp, cycles/step to the end of its pq:      ", " ".join(f"{v / nl:.0f}" for v in c[48:64]))
+if c[64:67].any():
+    nl = 6 * 50
+    print(f"  LU between the panels (warp 0, cycles/step): barrier {c[64] / nl:.0f}  U12 {c[65] / nl:.0f}  look-ahead tile update {c[66] / nl:.0f}")
 _native.lib().dpilqr_debug_backward_timing(None)
