@@ -134,7 +134,7 @@ def _cpu_sensitivity(job):
     return dict(k=k, trace_changes=int(trace_changes), moved=moved, moved_J=moved_J)
 
 
-def cpu_reference_run(n_scen, a, mode, first=0, keep=False):
+def cpu_reference_run(n_scen, a, mode, first=0, keep=False, pool=None):
     """iterations/s of the CPU oracle over `n_scen` scenarios on all host cores (scenario-level pool, one BLAS thread
     per worker -- the working equivalent of the reference's multiprocessing path)."""
     import multiprocessing as mp
@@ -146,13 +146,19 @@ def cpu_reference_run(n_scen, a, mode, first=0, keep=False):
     cores = os.cpu_count() or 1
     for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[var] = "1"
-    ctx = mp.get_context("spawn")
     jobs = [(k, a, mode) for k in range(first, first + n_scen)]
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, jobs[:min(cores, n_scen)])  # warm the workers (imports, dlopen)
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
+    try:
+        if own:
+            pool.map(_cpu_worker, jobs[:min(cores, n_scen)])  # warm the workers (imports, dlopen)
         t0 = time.perf_counter()
         res = pool.map(_cpu_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.terminate()
     iters = sum(r["iters"] for r in res)
     what = "Potential-iLQR (ilqrSolver.solve)" if mode == "potential" else "one DP-iLQR round (solve_distributed)"
     out = dict(value=iters / dt, unit=UNIT, cores=cores, kind="port", iterations=int(iters), seconds=dt,
@@ -171,11 +177,16 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     n_scen = args.cpu_scenarios or max(8 * cores, 64)
+    import multiprocessing as mp
+
+    for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
     vals = []
-    for step in range(args.warmup + args.steps):
-        res = cpu_reference_run(n_scen, args.agents, args.mode)
-        if step >= args.warmup:
-            vals.append(res)
+    with mp.get_context("spawn").Pool(cores) as pool:  # one pool of workers for all steps
+        for step in range(args.warmup + args.steps):
+            res = cpu_reference_run(n_scen, args.agents, args.mode, pool=pool)
+            if step >= args.warmup:
+                vals.append(res)
     value = sum(r["iterations"] for r in vals) / sum(r["seconds"] for r in vals)
     base = dict(vals[-1], value=value)
     base.pop("iterations"), base.pop("seconds")
