@@ -298,6 +298,15 @@ struct LaunchTimer {
     struct Rec { int kind; int units; cudaEvent_t e0, e1; };
     std::vector<Rec> recs;
     LaunchTimer(bool enable, cudaStream_t s) : on(enable), stream(s) {}
+    LaunchTimer(const LaunchTimer &) = delete;
+    LaunchTimer &operator=(const LaunchTimer &) = delete;
+    ~LaunchTimer()  // an error path that never reached flush(): the events still go back
+    {
+        for (auto &r : recs) {
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+    }
     void begin(int kind, int units)
     {
         if (!on) return;
