@@ -219,7 +219,12 @@ class CompiledBatch:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _dev(self, arr, shape):
-        t = arr if isinstance(arr, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64))
+        if not isinstance(arr, torch.Tensor):
+            arr = np.ascontiguousarray(arr, dtype=np.float64)
+            if not arr.flags.writeable:  # (read-only views, e.g. arrays of an .npz: torch wants a writable buffer)
+                arr = arr.copy()
+            arr = torch.from_numpy(arr)
+        t = arr
         t = t.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
         if tuple(t.shape) != tuple(shape):
             t = t.reshape(shape)
